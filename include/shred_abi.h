@@ -1,0 +1,138 @@
+/* include/shred_abi.h -- the drop-in boundary of the B200-native BPE trainer.
+ *
+ * libtrainer.so exports exactly the C ABI that the reference's ctypes binding resolves at import time
+ * (reference shredword/cbase.py:50-71): the 8 BPE entry points of shredword/csrc/bpe/bpe.h:62-72 with identical
+ * signatures, argument meaning and return conventions, plus the 13 Unigram symbols of
+ * shredword/csrc/unigram/unigram.h:50-68 as inert stubs (cbase.py binds them eagerly, so they must resolve; the
+ * Unigram trainer itself is out of scope).  Plain pointers and sizes only; no CUDA or torch
+ * types cross this boundary.
+ *
+ * The structs below re-express the reference's ABI-visible layouts (verified there with
+ * sizeof/offsetof on the reference build).  C/C++ consumers of the reference read some Trainer fields directly
+ * (shredword/csrc/trainer.cpp:100, test/bpe_test.cpp:69-72,112-121,151-161,186-196) -- those fields sit at the same
+ * offsets here and are kept up to date as host mirrors; everything else lives behind `impl`.
+ */
+#ifndef SHRED_ABI_H
+#define SHRED_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference bpe.h:43-48 -- 24 bytes: size_t@0, int32@8, float@12, uint64@16 */
+typedef struct BPEConfig {
+  size_t target_vocab_size;
+  int32_t unk_id;            /* id substituted for bytes dropped by character_coverage */
+  float character_coverage;  /* outside (0,1) => 0.995 (bpe.cpp:78) */
+  uint64_t min_pair_freq;    /* 0 => 2000 (bpe.cpp:79) */
+} BPEConfig;
+
+/* reference hash.h:27-29 */
+typedef struct PairKey { int32_t first, second; } PairKey;
+
+/* reference heap.h:17-21 -- 24 bytes */
+typedef struct BPEHeapEntry { PairKey key; uint64_t freq; uint32_t version; } BPEHeapEntry;
+
+/* reference heap.h:23-27 */
+typedef struct MaxHeap { BPEHeapEntry* data; size_t size; size_t cap; } MaxHeap;
+
+/* reference bpe.h:25-30 -- 32 bytes.  The symbols live in HBM here; corpus.words[i] points at a host placeholder. */
+typedef struct Symbol { int32_t id; struct Symbol* prev; struct Symbol* next; bool deleted; } Symbol;
+
+/* reference bpe.h:37-41 */
+typedef struct Corpus { Symbol** words; uint64_t* word_counts; size_t vocab_size; } Corpus;
+
+/* reference hash.h:42-45 (opaque here: the pair table is an open-addressing table in HBM) */
+typedef struct BIMap { void* buckets; size_t nbuckets; } BIMap;
+
+/* reference bpe.h:50-60 -- 128 bytes: config@0 heap@24 corpus@48 bigram_map@72 next_token@88 num_merges@96
+ * merge_ops@104 token_strs@112 token_freq@120.  `impl` is appended after the reference's last field. */
+typedef struct Trainer {
+  BPEConfig config;
+  MaxHeap heap;          /* host mirror of the exact replay heap (same 24-byte entries as the reference) */
+  Corpus corpus;         /* vocab_size = unique words; word_counts = host mirror; words[i] = non-NULL placeholder */
+  BIMap bigram_map;      /* nbuckets = live pair-table entries; buckets = NULL */
+  size_t next_token;     /* unused by the reference */
+  size_t num_merges;
+  PairKey* merge_ops;    /* merge m produced id 256+m from (first, second) */
+  char** token_strs;     /* unused by the reference */
+  uint64_t* token_freq;  /* unused by the reference */
+  void* impl;            /* B200 state (device buffers, streams, replay heap) */
+} Trainer;
+
+/* ---- BPE entry points: reference bpe.h:62-72 / bpe.cpp ------------------------------------------------------ */
+
+/* bpe.cpp:67-85.  Never returns NULL; exit(1) on a NULL config.  Copies the config, normalises coverage/min freq. */
+Trainer* create_trainer(const BPEConfig* config);
+/* bpe.cpp:87-96.  Releases host and device state.  Safe without a loaded corpus. */
+void bpe_trainer_destroy(Trainer* trainer);
+/* bpe.cpp:110-185.  0 on success, -1 on NULL arguments / unreadable file / allocation failure / CUDA failure.
+ * Tokens are maximal runs of bytes not in {\t,\r,\n,space}; a second load replaces the first. */
+int bpe_load_corpus(Trainer* trainer, const char* input_path);
+/* bpe.cpp:98-108.  Resets pair table and heap, then counts bigrams. */
+void bpe_init(Trainer* trainer);
+/* bpe.cpp:187-230.  Counts adjacent pairs into the pair table and seeds the heap (freq >= min_pair_freq). */
+void bpe_count_bigrams(Trainer* trainer);
+/* bpe.cpp:232-323.  Performs up to batch_size merges; returns merges done, 0 if the heap is empty, -1 on NULL. */
+int bpe_merge_batch(Trainer* trainer, int batch_size);
+/* bpe.cpp:345-386.  bpe_init + merge loop until vocab_size-256 merges or no pair reaches min_pair_freq.
+ * Returns merges performed by this call, -1 on NULL. */
+int bpe_train(Trainer* trainer);
+/* bpe.cpp:388-432.  vocab: "<token bytes> <freq>\n" x (256+M); model: M x {int32 a, int32 b, int32 256+m}. */
+void bpe_save(const Trainer* trainer, const char* model_path, const char* vocab_path);
+
+/* ---- extensions (not part of the reference ABI; never required by a drop-in consumer) ------------------------ */
+
+/* Same as bpe_load_corpus but from a host buffer (used by bench.py's end-to-end leg and the tests). */
+int bpe_b200_load_buffer(Trainer* trainer, const uint8_t* text, size_t n_bytes);
+/* Phase timers and work counters of the last load/train, see shred_stats_t. */
+typedef struct shred_stats_t {
+  uint64_t n_words, n_symbols_initial, n_symbols_live, n_slots, n_tokens, corpus_bytes;
+  uint64_t pair_entries, heap_size, heap_pushes, heap_pops;
+  uint64_t merges, occurrences, compactions;
+  uint64_t scan_launches;        /* merge-scan kernel launches in the last train */
+  double scan_device_ms;         /* sum of their CUDA-event durations */
+  double scan_bytes;             /* algorithmic bytes they covered: sum 4*(slots scanned) */
+  uint64_t count_launches; double count_device_ms; double count_bytes;
+  uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;
+  uint64_t kernel_launches;      /* every kernel launch since create */
+  double load_wall_ms, h2d_ms, train_wall_ms, host_heap_ms, wait_ms, save_wall_ms;
+  uint64_t h2d_bytes, d2h_bytes;
+} shred_stats_t;
+int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);
+/* Debug/parity getters: copy the current word table out of HBM.  word order = reference StrMap iteration order.
+ * ids_out receives the live symbol ids of all words back to back; off_out[n_words+1] their offsets. */
+int bpe_b200_get_words(const Trainer* trainer, uint64_t* counts_out, uint64_t* off_out, int32_t* ids_out, uint64_t ids_cap);
+/* Copies the keep mask (256 flags) and the unweighted byte histogram (256 counters) of the last load. */
+int bpe_b200_get_charset(const Trainer* trainer, uint8_t* keep_out, uint64_t* hist_out);
+/* Copies up to cap live pair-table entries as (first, second) + freq; returns the number of live entries. */
+uint64_t bpe_b200_get_pairs(const Trainer* trainer, int32_t* ab_out, uint64_t* freq_out, uint64_t cap);
+/* Human-readable description of the device the trainer runs on ("NVIDIA B200 sm_100 148 SMs"). */
+const char* bpe_b200_device_name(void);
+
+/* ---- Unigram symbols: reference unigram.h:50-68.  Stubs; every call reports failure. -------------------------- */
+typedef struct UnigramTrainer UnigramTrainer;
+UnigramTrainer* trainerCreate(int vocab_size, float character_coverage, int max_len, int seed_size); /* returns NULL */
+void trainerDestroy(UnigramTrainer* trainer);
+bool addTextToTrainer(UnigramTrainer* trainer, const char* text);
+bool preprocessTexts(UnigramTrainer* trainer);
+bool extractInitialSubwords(UnigramTrainer* trainer);
+float computeLoss(UnigramTrainer* trainer, const char** texts, int text_count);
+double computeTokenLoss(UnigramTrainer* trainer, const char* token, const char** texts, int text_count);
+bool pruneVocabStep(UnigramTrainer* trainer, const char** texts, int text_count, double reduction_ratio);
+bool updateTokenScores(UnigramTrainer* trainer, const char** texts, int text_count);
+bool trainUnigram(UnigramTrainer* trainer, const char** texts, int text_count, int num_iterations);
+bool getVocab(UnigramTrainer* trainer, char*** tokens, double** scores, int* count);
+bool saveVocab(UnigramTrainer* trainer, const char* filepath);
+bool loadVocab(UnigramTrainer* trainer, const char* filepath);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHRED_ABI_H */

@@ -1,0 +1,74 @@
+// engine.hpp -- the seam between the sequential host control (exact heap replay, trainer_core.cpp) and the
+// data-parallel device work (CUDA kernels, cuda/engine_cuda.cu).
+//
+// The product library links exactly one implementation: the CUDA engine.  tests/hostsim/ holds a CPU stand-in of
+// this interface that exists only so the *host* logic (ordering, versions, phantom pairs, heap replay) can be
+// checked against the reference on machines without a GPU; it is never linked into libtrainer.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace shred {
+
+// One record per pair key touched by a device pass, returned UNORDERED; the host orders them.
+//   count pass : kind=PUSH,    val = freq            seq = flat position of the pair's first sighting   (Appendix A6/A7)
+//   merge pass : kind=PUSH,    val = new table freq  (>= min_pair_freq)                                   (A11)
+//                kind=DEMOTE,  val = new table freq  (fell from >= min to < min; heap entry must die)     (A9 "< min")
+//                kind=PHANTOM, val = net delta (two's complement int64) of a key that contains unk_id     (A12)
+//                seq = smallest (flat position*4 + slot) at which the reference's FreqChangeMap first saw the key (A14)
+struct Rec {
+  uint64_t key;  // ((uint64)first << 32) | (uint64)second with both int32 sign-extended (reference bpe.cpp:277-278)
+  uint64_t val;
+  uint64_t seq;
+  uint32_t kind;
+  uint32_t pad;
+};
+enum : uint32_t { REC_PUSH = 0, REC_DEMOTE = 1, REC_PHANTOM = 2 };
+
+struct EngineConfig {
+  int32_t unk_id;
+  float coverage;     // already normalised
+  uint64_t min_freq;  // already normalised
+};
+
+struct LoadInfo {
+  uint64_t n_words, n_symbols, n_tokens;
+  uint64_t hist[256];
+  uint8_t keep[256];
+  uint32_t n_distinct, n_keep;
+};
+
+struct EngineStats {
+  uint64_t n_slots, n_symbols_live, pair_entries, compactions;
+  uint64_t scan_launches; double scan_device_ms; double scan_bytes;
+  uint64_t count_launches; double count_device_ms; double count_bytes;
+  uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;
+  uint64_t kernel_launches;
+  double h2d_ms, wait_ms;
+  uint64_t h2d_bytes, d2h_bytes;
+};
+
+class Engine {
+ public:
+  virtual ~Engine() {}
+  // Tokenise `text`, build the unique-word table in reference order, apply character coverage, lay the symbols out.
+  // A second load replaces the first.  Returns 0 or -1.
+  virtual int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) = 0;
+  // Reset the pair table, count all adjacent non-unk pairs; *recs = PUSH records for entries with freq >= min.
+  virtual int count_pairs(const Rec** recs, size_t* n) = 0;
+  // Rewrite every leftmost non-overlapping (a,b) -> new_id, update the pair table, return the touched keys.
+  virtual int merge(int32_t a, int32_t b, int32_t new_id, const Rec** recs, size_t* n, uint64_t* occurrences) = 0;
+  // freq[id] += word_count over all live symbols with 0 <= id < n_tokens (reference bpe.cpp:409-415).
+  virtual int token_freqs(uint64_t* freq, size_t n_tokens) = 0;
+  virtual int word_counts(uint64_t* out) = 0;  // host mirror of Corpus.word_counts
+  // parity/debug getters
+  virtual int get_words(uint64_t* counts, uint64_t* off, int32_t* ids, uint64_t ids_cap) = 0;
+  virtual uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) = 0;
+  virtual void stats(EngineStats* out) = 0;
+  virtual const char* name() = 0;
+};
+
+// Implemented by cuda/engine_cuda.cu.  Fails loudly (message on stderr, returns nullptr) without a usable GPU.
+Engine* make_device_engine();
+
+}  // namespace shred

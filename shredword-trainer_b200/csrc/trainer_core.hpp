@@ -1,0 +1,54 @@
+// trainer_core.hpp -- host control of the B200 BPE trainer: everything in the reference's train loop that is
+// inherently sequential (exact heap replay, push ordering, lazy-invalidation versions, phantom unk pairs), driving an
+// Engine for everything that is data parallel.  See trainer_core.cpp for the reference file:line map.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/shred_abi.h"
+#include "engine.hpp"
+#include "exact_heap.hpp"
+#include "flat_map.hpp"
+
+namespace shred {
+
+class TrainerCore {
+ public:
+  TrainerCore(Trainer* abi, Engine* eng);
+  ~TrainerCore();
+
+  int load_file(const char* path);
+  int load_buffer(const uint8_t* text, size_t n);
+  void count_bigrams();
+  void init();
+  int merge_batch(int batch_size);
+  int train();
+  void save(const char* model_path, const char* vocab_path);
+  void get_stats(shred_stats_t* out);
+  Engine* engine() { return eng_; }
+  const LoadInfo& load_info() const { return info_; }
+  bool loaded() const { return loaded_; }
+
+ private:
+  void sync_mirrors();
+  bool is_phantom(int32_t a, int32_t b) const { return a == abi_->config.unk_id || b == abi_->config.unk_id; }
+  void apply_records(const Rec* recs, size_t n);
+
+  Trainer* abi_;
+  Engine* eng_;
+  ExactHeap heap_;
+  FlatMap<uint32_t> version_;   // pair key -> current version (absent = 0)
+  FlatMap<uint64_t> phantom_;   // pair keys containing unk_id -> freq as the reference's table would hold it
+  std::vector<Rec> order_;      // scratch: records in application order
+  LoadInfo info_;
+  bool loaded_ = false;
+  size_t merge_cap_ = 0;
+  Symbol placeholder_;
+  // statistics of the last load/train
+  uint64_t occurrences_ = 0, merges_last_ = 0, corpus_bytes_ = 0;
+  double load_wall_ms_ = 0, train_wall_ms_ = 0, host_heap_ms_ = 0, save_wall_ms_ = 0;
+  bool log_merges_ = false, quiet_ = false;
+};
+
+}  // namespace shred

@@ -1,0 +1,166 @@
+// tests/hostsim/engine_hostsim.cpp -- TEST INFRASTRUCTURE, never part of libtrainer.so.
+//
+// A deliberately naive CPU stand-in for the device engine (shredword-trainer_b200/csrc/engine.hpp).  It exists so
+// that the HOST control logic of the product (trainer_core.cpp: push ordering, versions, phantom pairs, exact heap
+// replay) can be checked against the reference on a machine without a GPU.  It produces the same kind of records
+// the CUDA kernels produce -- and shuffles them, because the kernels emit them in nondeterministic order.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../shredword-trainer_b200/csrc/charset.hpp"
+#include "../../shredword-trainer_b200/csrc/engine.hpp"
+
+namespace shred {
+
+namespace {
+inline bool is_delim(uint8_t c) { return c == '\t' || c == '\r' || c == '\n' || c == ' '; }
+inline uint64_t fc_key(int32_t a, int32_t b) { return (static_cast<uint64_t>(static_cast<int64_t>(a)) << 32) | static_cast<uint64_t>(static_cast<int64_t>(b)); }
+
+class HostSimEngine : public Engine {
+ public:
+  int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) override {
+    cfg_ = cfg;
+    std::unordered_map<std::string, size_t> idx;
+    struct W { std::string s; uint64_t count; uint32_t bucket; size_t first; };
+    std::vector<W> ws;
+    size_t i = 0, ntok = 0;
+    while (i < n) {
+      while (i < n && is_delim(text[i])) i++;
+      size_t s = i;
+      while (i < n && !is_delim(text[i])) i++;
+      if (i > s) {
+        std::string w(reinterpret_cast<const char*>(text + s), i - s);
+        ntok++;
+        auto it = idx.find(w);
+        if (it == idx.end()) {
+          uint64_t dj = 5381;
+          for (unsigned char c : w) dj = dj * 33 + c;
+          idx.emplace(w, ws.size());
+          ws.push_back(W{w, 1, static_cast<uint32_t>(dj & 4095), s});
+        } else ws[it->second].count++;
+      }
+    }
+    std::stable_sort(ws.begin(), ws.end(), [](const W& a, const W& b) { return a.bucket != b.bucket ? a.bucket < b.bucket : a.first < b.first; });
+    std::memset(info, 0, sizeof *info);
+    for (auto& w : ws) for (unsigned char c : w.s) info->hist[c]++;
+    charset_keep(info->hist, cfg.coverage, info->keep, &info->n_distinct, &info->n_keep);
+    words_.clear(); counts_.clear();
+    uint64_t S = 0;
+    for (auto& w : ws) {
+      std::vector<int32_t> ids;
+      for (unsigned char c : w.s) ids.push_back(info->keep[c] ? static_cast<int32_t>(c) : cfg.unk_id);
+      S += ids.size();
+      words_.push_back(std::move(ids)); counts_.push_back(w.count);
+    }
+    info->n_words = words_.size(); info->n_symbols = S; info->n_tokens = ntok;
+    table_.clear();
+    return 0;
+  }
+
+  int count_pairs(const Rec** recs, size_t* n) override {
+    table_.clear();
+    std::unordered_map<uint64_t, uint64_t> first;
+    uint64_t p = 0;
+    for (size_t wi = 0; wi < words_.size(); wi++) {
+      p++;  // header slot
+      auto& s = words_[wi];
+      for (size_t j = 0; j < s.size(); j++, p++) {
+        if (j + 1 >= s.size() || s[j] == cfg_.unk_id || s[j + 1] == cfg_.unk_id) continue;
+        uint64_t k = fc_key(s[j], s[j + 1]);
+        table_[k] += counts_[wi];
+        if (!first.count(k)) first[k] = p;
+      }
+    }
+    out_.clear();
+    for (auto& kv : table_) if (kv.second >= cfg_.min_freq) out_.push_back(Rec{kv.first, kv.second, first[kv.first], REC_PUSH, 0});
+    std::shuffle(out_.begin(), out_.end(), rng_);
+    *recs = out_.data(); *n = out_.size();
+    return 0;
+  }
+
+  int merge(int32_t A, int32_t B, int32_t N, const Rec** recs, size_t* n, uint64_t* occurrences) override {
+    struct Agg { int64_t delta; uint64_t seq; };
+    std::unordered_map<uint64_t, Agg> agg;
+    auto add = [&](uint64_t k, int64_t d, uint64_t seq) {
+      auto it = agg.find(k);
+      if (it == agg.end()) agg.emplace(k, Agg{d, seq}); else { it->second.delta += d; it->second.seq = std::min(it->second.seq, seq); }
+    };
+    uint64_t occ = 0, p = 0;
+    for (size_t wi = 0; wi < words_.size(); wi++) {
+      auto& s = words_[wi];
+      uint64_t base = p + 1;  // flat position of the word's first symbol in the (uncompacted) layout of this pass
+      p += 1 + s.size();
+      int64_t c = static_cast<int64_t>(counts_[wi]);
+      size_t r = 0, w = 0;
+      while (r < s.size()) {
+        if (r + 1 < s.size() && s[r] == A && s[r + 1] == B) {
+          uint64_t seq = (base + r) * 4;
+          occ++;
+          if (w > 0) { add(fc_key(s[w - 1], A), -c, seq + 0); add(fc_key(s[w - 1], N), c, seq + 1); }
+          if (r + 2 < s.size()) { add(fc_key(B, s[r + 2]), -c, seq + 2); add(fc_key(N, s[r + 2]), c, seq + 3); }
+          s[w++] = N; r += 2;
+        } else s[w++] = s[r++];
+      }
+      s.resize(w);
+    }
+    out_.clear();
+    for (auto& kv : agg) {
+      int32_t pa = static_cast<int32_t>(kv.first >> 32), pb = static_cast<int32_t>(kv.first & 0xFFFFFFFFu);
+      if (pa == A && pb == B) continue;
+      if (pa == cfg_.unk_id || pb == cfg_.unk_id) { out_.push_back(Rec{kv.first, static_cast<uint64_t>(kv.second.delta), kv.second.seq, REC_PHANTOM, 0}); continue; }
+      uint64_t& f = table_[kv.first];
+      uint64_t old = f;
+      int64_t d = kv.second.delta;
+      if (d < 0) { uint64_t ad = static_cast<uint64_t>(-d); f = f >= ad ? f - ad : 0; } else f += static_cast<uint64_t>(d);
+      if (f >= cfg_.min_freq) out_.push_back(Rec{kv.first, f, kv.second.seq, REC_PUSH, 0});
+      else if (old >= cfg_.min_freq) out_.push_back(Rec{kv.first, f, kv.second.seq, REC_DEMOTE, 0});
+    }
+    table_[fc_key(A, B)] = 0;
+    std::shuffle(out_.begin(), out_.end(), rng_);
+    *recs = out_.data(); *n = out_.size(); *occurrences = occ;
+    return 0;
+  }
+
+  int token_freqs(uint64_t* freq, size_t T) override {
+    for (size_t wi = 0; wi < words_.size(); wi++) for (int32_t id : words_[wi]) if (id >= 0 && static_cast<size_t>(id) < T) freq[id] += counts_[wi];
+    return 0;
+  }
+  int word_counts(uint64_t* out) override { std::copy(counts_.begin(), counts_.end(), out); return 0; }
+  int get_words(uint64_t* counts, uint64_t* off, int32_t* ids, uint64_t cap) override {
+    uint64_t at = 0;
+    for (size_t wi = 0; wi < words_.size(); wi++) {
+      if (counts) counts[wi] = counts_[wi];
+      if (off) off[wi] = at;
+      for (int32_t id : words_[wi]) { if (ids && at < cap) ids[at] = id; at++; }
+    }
+    if (off) off[words_.size()] = at;
+    return 0;
+  }
+  uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) override {
+    uint64_t i = 0;
+    for (auto& kv : table_) { if (i < cap) { ab[2 * i] = static_cast<int32_t>(kv.first >> 32); ab[2 * i + 1] = static_cast<int32_t>(kv.first & 0xFFFFFFFFu); freq[i] = kv.second; } i++; }
+    return i;
+  }
+  void stats(EngineStats* out) override { std::memset(out, 0, sizeof *out); out->pair_entries = table_.size(); }
+  const char* name() override { return "hostsim (CPU stand-in, tests only)"; }
+
+ private:
+  EngineConfig cfg_{};
+  std::vector<std::vector<int32_t>> words_;
+  std::vector<uint64_t> counts_;
+  std::unordered_map<uint64_t, uint64_t> table_;
+  std::vector<Rec> out_;
+  std::mt19937_64 rng_{12345};
+};
+}  // namespace
+
+Engine* make_device_engine() { return new HostSimEngine(); }
+
+}  // namespace shred
+
+extern "C" const char* bpe_b200_device_name(void) { return "hostsim"; }
