@@ -21,6 +21,12 @@
 #include <stdbool.h>
 #endif
 
+#if defined(__GNUC__)
+#define SHRED_API __attribute__((visibility("default")))
+#else
+#define SHRED_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -69,28 +75,28 @@ typedef struct Trainer {
 /* ---- BPE entry points: reference bpe.h:62-72 / bpe.cpp ------------------------------------------------------ */
 
 /* bpe.cpp:67-85.  Never returns NULL; exit(1) on a NULL config.  Copies the config, normalises coverage/min freq. */
-Trainer* create_trainer(const BPEConfig* config);
+SHRED_API Trainer* create_trainer(const BPEConfig* config);
 /* bpe.cpp:87-96.  Releases host and device state.  Safe without a loaded corpus. */
-void bpe_trainer_destroy(Trainer* trainer);
+SHRED_API void bpe_trainer_destroy(Trainer* trainer);
 /* bpe.cpp:110-185.  0 on success, -1 on NULL arguments / unreadable file / allocation failure / CUDA failure.
  * Tokens are maximal runs of bytes not in {\t,\r,\n,space}; a second load replaces the first. */
-int bpe_load_corpus(Trainer* trainer, const char* input_path);
+SHRED_API int bpe_load_corpus(Trainer* trainer, const char* input_path);
 /* bpe.cpp:98-108.  Resets pair table and heap, then counts bigrams. */
-void bpe_init(Trainer* trainer);
+SHRED_API void bpe_init(Trainer* trainer);
 /* bpe.cpp:187-230.  Counts adjacent pairs into the pair table and seeds the heap (freq >= min_pair_freq). */
-void bpe_count_bigrams(Trainer* trainer);
+SHRED_API void bpe_count_bigrams(Trainer* trainer);
 /* bpe.cpp:232-323.  Performs up to batch_size merges; returns merges done, 0 if the heap is empty, -1 on NULL. */
-int bpe_merge_batch(Trainer* trainer, int batch_size);
+SHRED_API int bpe_merge_batch(Trainer* trainer, int batch_size);
 /* bpe.cpp:345-386.  bpe_init + merge loop until vocab_size-256 merges or no pair reaches min_pair_freq.
  * Returns merges performed by this call, -1 on NULL. */
-int bpe_train(Trainer* trainer);
+SHRED_API int bpe_train(Trainer* trainer);
 /* bpe.cpp:388-432.  vocab: "<token bytes> <freq>\n" x (256+M); model: M x {int32 a, int32 b, int32 256+m}. */
-void bpe_save(const Trainer* trainer, const char* model_path, const char* vocab_path);
+SHRED_API void bpe_save(const Trainer* trainer, const char* model_path, const char* vocab_path);
 
 /* ---- extensions (not part of the reference ABI; never required by a drop-in consumer) ------------------------ */
 
 /* Same as bpe_load_corpus but from a host buffer (used by bench.py's end-to-end leg and the tests). */
-int bpe_b200_load_buffer(Trainer* trainer, const uint8_t* text, size_t n_bytes);
+SHRED_API int bpe_b200_load_buffer(Trainer* trainer, const uint8_t* text, size_t n_bytes);
 /* Phase timers and work counters of the last load/train, see shred_stats_t. */
 typedef struct shred_stats_t {
   uint64_t n_words, n_symbols_initial, n_symbols_live, n_slots, n_tokens, corpus_bytes;
@@ -105,32 +111,32 @@ typedef struct shred_stats_t {
   double load_wall_ms, h2d_ms, train_wall_ms, host_heap_ms, wait_ms, save_wall_ms;
   uint64_t h2d_bytes, d2h_bytes;
 } shred_stats_t;
-int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);
+SHRED_API int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);
 /* Debug/parity getters: copy the current word table out of HBM.  word order = reference StrMap iteration order.
  * ids_out receives the live symbol ids of all words back to back; off_out[n_words+1] their offsets. */
-int bpe_b200_get_words(const Trainer* trainer, uint64_t* counts_out, uint64_t* off_out, int32_t* ids_out, uint64_t ids_cap);
+SHRED_API int bpe_b200_get_words(const Trainer* trainer, uint64_t* counts_out, uint64_t* off_out, int32_t* ids_out, uint64_t ids_cap);
 /* Copies the keep mask (256 flags) and the unweighted byte histogram (256 counters) of the last load. */
-int bpe_b200_get_charset(const Trainer* trainer, uint8_t* keep_out, uint64_t* hist_out);
+SHRED_API int bpe_b200_get_charset(const Trainer* trainer, uint8_t* keep_out, uint64_t* hist_out);
 /* Copies up to cap live pair-table entries as (first, second) + freq; returns the number of live entries. */
-uint64_t bpe_b200_get_pairs(const Trainer* trainer, int32_t* ab_out, uint64_t* freq_out, uint64_t cap);
+SHRED_API uint64_t bpe_b200_get_pairs(const Trainer* trainer, int32_t* ab_out, uint64_t* freq_out, uint64_t cap);
 /* Human-readable description of the device the trainer runs on ("NVIDIA B200 sm_100 148 SMs"). */
-const char* bpe_b200_device_name(void);
+SHRED_API const char* bpe_b200_device_name(void);
 
 /* ---- Unigram symbols: reference unigram.h:50-68.  Stubs; every call reports failure. -------------------------- */
 typedef struct UnigramTrainer UnigramTrainer;
-UnigramTrainer* trainerCreate(int vocab_size, float character_coverage, int max_len, int seed_size); /* returns NULL */
-void trainerDestroy(UnigramTrainer* trainer);
-bool addTextToTrainer(UnigramTrainer* trainer, const char* text);
-bool preprocessTexts(UnigramTrainer* trainer);
-bool extractInitialSubwords(UnigramTrainer* trainer);
-float computeLoss(UnigramTrainer* trainer, const char** texts, int text_count);
-double computeTokenLoss(UnigramTrainer* trainer, const char* token, const char** texts, int text_count);
-bool pruneVocabStep(UnigramTrainer* trainer, const char** texts, int text_count, double reduction_ratio);
-bool updateTokenScores(UnigramTrainer* trainer, const char** texts, int text_count);
-bool trainUnigram(UnigramTrainer* trainer, const char** texts, int text_count, int num_iterations);
-bool getVocab(UnigramTrainer* trainer, char*** tokens, double** scores, int* count);
-bool saveVocab(UnigramTrainer* trainer, const char* filepath);
-bool loadVocab(UnigramTrainer* trainer, const char* filepath);
+SHRED_API UnigramTrainer* trainerCreate(int vocab_size, float character_coverage, int max_len, int seed_size); /* returns NULL */
+SHRED_API void trainerDestroy(UnigramTrainer* trainer);
+SHRED_API bool addTextToTrainer(UnigramTrainer* trainer, const char* text);
+SHRED_API bool preprocessTexts(UnigramTrainer* trainer);
+SHRED_API bool extractInitialSubwords(UnigramTrainer* trainer);
+SHRED_API float computeLoss(UnigramTrainer* trainer, const char** texts, int text_count);
+SHRED_API double computeTokenLoss(UnigramTrainer* trainer, const char* token, const char** texts, int text_count);
+SHRED_API bool pruneVocabStep(UnigramTrainer* trainer, const char** texts, int text_count, double reduction_ratio);
+SHRED_API bool updateTokenScores(UnigramTrainer* trainer, const char** texts, int text_count);
+SHRED_API bool trainUnigram(UnigramTrainer* trainer, const char** texts, int text_count, int num_iterations);
+SHRED_API bool getVocab(UnigramTrainer* trainer, char*** tokens, double** scores, int* count);
+SHRED_API bool saveVocab(UnigramTrainer* trainer, const char* filepath);
+SHRED_API bool loadVocab(UnigramTrainer* trainer, const char* filepath);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,1047 @@
+// engine_cuda.cu -- the B200 (sm_100a) device engine of the BPE trainer: corpus ingest, pair counting, merge
+// application and pair-table maintenance as hand-written CUDA kernels.  Implements shred::Engine (../engine.hpp).
+//
+// Data layout in HBM
+//   ids[]   int32, one flat array holding every unique word back to back in reference word order (A3):
+//             [HDR|wi] s0 s1 ... s(len-1) [DEAD ...]          HDR|wi < -1, symbols >= 0, DEAD == -1
+//           A word keeps its slot between compactions; merges left-pack its live symbols and fill the tail with DEAD.
+//           Because words are stored in reference scan order, "flat position" is monotone in the reference's
+//           (word index, position) order and serves as the sequence number the host needs (Appendix A14).
+//   wcnt[]  uint64 word counts, woff[] uint64 slot offsets (N+1), wlen[] uint32 live lengths.
+//   pair table   open addressing, uint64 key (first<<32|second) -> uint64 freq        (reference BIMap, hash.cpp:104-130)
+//   delta table  open addressing scratch, key -> (sum of +/-count, min sequence)      (reference FreqChangeMap, bpe.cpp:9-38)
+//
+// Kernels (reference loop each one replaces)
+//   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise on \t\r\n space, unique-word table insert
+//   k_hist ............ histogram.cpp:30-36                unweighted byte histogram over unique words
+//   k_scatter/k_rank .. hash.cpp:61-72                     word order = (djb2 & 4095, first occurrence)
+//   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids with unk substitution
+//   k_count ........... bpe.cpp:187-218                    adjacent pair counts
+//   k_detect .......... bpe.cpp:265-273                    HBM-bound scan for occurrences of the chosen pair
+//   k_apply ........... bpe.cpp:274-296                    rewrite + emit count deltas
+//   k_finalize ........ bpe.cpp:297-318                    aggregate deltas into the pair table, emit records
+//   k_token_freq ...... bpe.cpp:409-415                    final token frequencies
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../../include/shred_abi.h"
+#include "../charset.hpp"
+#include "../engine.hpp"
+
+namespace shred {
+namespace {
+
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      std::fprintf(stderr, "[ERROR]\t CUDA: %s -> %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return -1;                                                                                              \
+    }                                                                                                         \
+  } while (0)
+
+#define RC(call)            \
+  do {                      \
+    int rc_ = (call);       \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+typedef unsigned long long ull;
+
+constexpr int32_t DEAD = -1;
+constexpr uint32_t HDR_BIT = 0x80000000u;
+constexpr int32_t UNK_CODE_NEG = 0x7FFFFFFF;  // stored code of unk symbols when unk_id < 0
+constexpr uint64_t PT_EMPTY = ~0ull;
+constexpr uint64_t SEQ_MAX = ~0ull;
+constexpr int N_SM_FALLBACK = 148;
+
+enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16 };
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ bool is_delim(uint32_t c) { return c <= 32u && ((0x100002600ull >> c) & 1ull); }  // \t \n \r space
+__device__ __forceinline__ uint64_t fc_key(int32_t a, int32_t b) {  // bpe.cpp:277-278: both operands sign-extend
+  return (static_cast<uint64_t>(static_cast<int64_t>(a)) << 32) | static_cast<uint64_t>(static_cast<int64_t>(b));
+}
+
+struct Ctrl {  // mapped pinned host memory, written by the last block of k_finalize
+  volatile uint64_t flag;
+  uint64_t n_recs, occ, pt_n, n_leaders, n_keys;
+  uint32_t err, pad;
+};
+
+struct DevCounters {  // device memory
+  uint32_t wl_n, dt_n, rec_n, blocks_done;
+  ull occ;
+  ull pt_n;
+  uint32_t err, pad;
+  ull n_tokens;
+  uint32_t n_unique, pad2;
+};
+
+struct DeltaTable {
+  uint64_t* keys; ull* delta; ull* seq; uint32_t* list;
+  uint64_t mask; uint64_t empty; uint32_t cap;
+};
+struct PairTable {
+  uint64_t* keys; ull* freq;
+  uint64_t mask; uint64_t cap;
+};
+
+// ------------------------------------------------------------------------------------------------ hash-table helpers
+
+__device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, uint64_t key, int64_t delta, uint64_t seq) {
+  uint64_t slot = mix64(key) & dt.mask;
+  for (uint32_t probe = 0; probe < dt.cap; ++probe) {
+    uint64_t cur = dt.keys[slot];
+    if (cur == dt.empty) {
+      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot]), static_cast<ull>(dt.empty), static_cast<ull>(key));
+      if (prev == dt.empty) {
+        uint32_t idx = atomicAdd(&ctr->dt_n, 1u);
+        if (idx < dt.cap) dt.list[idx] = static_cast<uint32_t>(slot);
+        cur = key;
+      } else cur = prev;
+    }
+    if (cur == key) {
+      atomicAdd(&dt.delta[slot], static_cast<ull>(delta));
+      atomicMin(&dt.seq[slot], static_cast<ull>(seq));
+      return;
+    }
+    slot = (slot + 1) & dt.mask;
+  }
+  atomicOr(&ctr->err, ERR_DT_FULL);
+}
+
+// returns the slot of `key`, inserting it with freq 0 if absent
+__device__ __forceinline__ uint64_t pt_slot(const PairTable& pt, DevCounters* ctr, uint64_t key) {
+  uint64_t slot = mix64(key) & pt.mask;
+  for (uint64_t probe = 0; probe < pt.cap; ++probe) {
+    uint64_t cur = pt.keys[slot];
+    if (cur == PT_EMPTY) {
+      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.keys[slot]), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
+      if (prev == PT_EMPTY) { atomicAdd(&ctr->pt_n, 1ull); return slot; }
+      cur = prev;
+    }
+    if (cur == key) return slot;
+    slot = (slot + 1) & pt.mask;
+  }
+  atomicOr(&ctr->err, ERR_PT_FULL);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------ ingest
+
+struct WordTable {
+  ull* tag;       // 0 = empty
+  ull* first;     // smallest byte offset of an occurrence
+  ull* count;
+  uint32_t* len;
+  uint32_t* bucket;  // djb2 & 4095
+  uint64_t mask, cap;
+};
+
+// Each thread owns 16 consecutive corpus bytes (one uint4 load) and inserts every token that STARTS inside them.
+// text is padded with >= 32 spaces, so token walks terminate.
+__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
+  const uint64_t n16 = (n + 15) >> 4;
+  uint32_t my_tokens = 0;
+  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n16; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t base = t << 4;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t prev = base ? text[base - 1] : 32u;
+    // delimiter mask of my 16 bytes
+    uint32_t dm = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 255u; dm |= (is_delim(c) ? 1u : 0u) << i; }
+    uint32_t starts = ~dm & ((dm << 1) | (is_delim(prev) ? 1u : 0u)) & 0xFFFFu;
+    while (starts) {
+      const int i = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint64_t off = base + i;
+      if (off >= n) break;
+      // walk the token: two 32-bit multiplicative hashes (placement tag) + djb2 (reference bucket, hash.cpp:35-39)
+      uint32_t h1 = 2166136261u ^ seed, h2 = 0x9E3779B9u + seed, dj = 5381u, len = 0;
+      for (;;) {
+        const uint32_t c = text[off + len];
+        if (is_delim(c)) break;
+        h1 = (h1 ^ c) * 16777619u;
+        h2 = (h2 + c) * 0x85EBCA6Bu; h2 ^= h2 >> 15;
+        dj = dj * 33u + c;
+        ++len;
+      }
+      ++my_tokens;
+      const uint64_t tag = mix64((static_cast<uint64_t>(h1) << 32) | h2 | 0) | 1ull;
+      uint64_t slot = tag & wt.mask;
+      bool done = false;
+      for (uint32_t probe = 0; probe < 8192u && !done; ++probe) {
+        ull cur = wt.tag[slot];
+        if (cur == 0ull) {
+          ull prevt = atomicCAS(&wt.tag[slot], 0ull, static_cast<ull>(tag));
+          if (prevt == 0ull) {  // claimed: publish the immutable facts
+            wt.len[slot] = len;
+            wt.bucket[slot] = dj & 4095u;
+            atomicAdd(&ctr->n_unique, 1u);
+            cur = tag;
+          } else cur = prevt;
+        }
+        if (cur == tag) {
+          const ull old = atomicMin(&wt.first[slot], static_cast<ull>(off));
+          atomicAdd(&wt.count[slot], 1ull);
+          if (old != SEQ_MAX && old != off) {  // same tag: must be the same bytes, else retry ingest with a new seed
+            bool same = is_delim(text[old + len]);
+            for (uint32_t j = 0; j < len && same; j++) same = text[old + j] == text[off + j];
+            if (!same) atomicOr(&ctr->err, ERR_WT_COLLISION);
+          }
+          done = true;
+        } else slot = (slot + 1) & wt.mask;
+      }
+      if (!done) atomicOr(&ctr->err, ERR_WT_FULL);
+    }
+  }
+  // token count: warp reduce, one atomic per warp
+  for (int o = 16; o; o >>= 1) my_tokens += __shfl_down_sync(0xFFFFFFFFu, my_tokens, o);
+  if ((threadIdx.x & 31) == 0 && my_tokens) atomicAdd(&ctr->n_tokens, static_cast<ull>(my_tokens));
+}
+
+// unique slots -> dense list + per-bucket population
+__global__ void k_collect(WordTable wt, uint32_t* u_slot, uint32_t* u_n, uint32_t* bucket_cnt) {
+  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < wt.cap; s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (wt.tag[s] != 0ull) {
+      uint32_t idx = atomicAdd(u_n, 1u);
+      u_slot[idx] = static_cast<uint32_t>(s);
+      atomicAdd(&bucket_cnt[wt.bucket[s]], 1u);
+    }
+  }
+}
+
+// exclusive scan of 4096 bucket counts by one block of 1024 threads
+__global__ void k_scan4096(const uint32_t* cnt, uint32_t* start) {
+  __shared__ uint32_t part[1024];
+  const int t = threadIdx.x;
+  uint32_t c[4], s = 0;
+  for (int i = 0; i < 4; i++) { c[i] = cnt[t * 4 + i]; s += c[i]; }
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) { uint32_t v = t >= o ? part[t - o] : 0; __syncthreads(); part[t] += v; __syncthreads(); }
+  uint32_t run = part[t] - s;
+  for (int i = 0; i < 4; i++) { start[t * 4 + i] = run; run += c[i]; }
+  if (t == 1023) start[4096] = run;
+}
+
+__global__ void k_scatter(WordTable wt, const uint32_t* u_slot, uint32_t n, const uint32_t* bstart, uint32_t* cursor, uint32_t* tmp_slot, ull* tmp_first) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = u_slot[i], b = wt.bucket[s];
+    const uint32_t pos = bstart[b] + atomicAdd(&cursor[b], 1u);
+    tmp_slot[pos] = s;
+    tmp_first[pos] = wt.first[s];
+  }
+}
+
+// rank of each word inside its bucket by first occurrence (all first offsets are distinct): wi = bucket_start + rank
+__global__ void k_rank(WordTable wt, const uint32_t* tmp_slot, const ull* tmp_first, uint32_t n, const uint32_t* bstart, uint32_t* order_slot) {
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t s = tmp_slot[e], b = wt.bucket[s];
+    const uint32_t bs = bstart[b], be = bstart[b + 1];
+    const ull mine = tmp_first[e];
+    uint32_t rank = 0;
+    for (uint32_t j = bs; j < be; j++) rank += tmp_first[j] < mine ? 1u : 0u;
+    order_slot[bs + rank] = s;
+  }
+}
+
+// unweighted byte histogram over unique words (histogram.cpp:30-36) + per-word facts in reference order
+__global__ void __launch_bounds__(256) k_hist_words(const uint8_t* __restrict__ text, WordTable wt, const uint32_t* order_slot, uint32_t n,
+                                                    ull* hist, ull* wcnt, uint32_t* wlen, ull* len1) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
+    const uint32_t s = order_slot[wi];
+    const uint32_t len = wt.len[s];
+    const ull first = wt.first[s];
+    wcnt[wi] = wt.count[s];
+    wlen[wi] = len;
+    len1[wi] = static_cast<ull>(len) + 1ull;
+    for (uint32_t j = 0; j < len; j++) atomicAdd(&sh[text[first + j]], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<ull>(sh[threadIdx.x]));
+}
+
+__global__ void __launch_bounds__(256) k_symbolize(const uint8_t* __restrict__ text, WordTable wt, const uint32_t* order_slot, uint32_t n,
+                                                   const ull* woff, const uint8_t* keep, int32_t unk_code, int32_t* ids) {
+  __shared__ uint8_t sk[256];
+  sk[threadIdx.x] = keep[threadIdx.x];
+  __syncthreads();
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
+    const uint32_t s = order_slot[wi];
+    const uint32_t len = wt.len[s];
+    const ull first = wt.first[s];
+    const ull base = woff[wi];
+    ids[base] = static_cast<int32_t>(HDR_BIT | wi);
+    for (uint32_t j = 0; j < len; j++) { const uint32_t c = text[first + j]; ids[base + 1 + j] = sk[c] ? static_cast<int32_t>(c) : unk_code; }
+  }
+}
+
+__global__ void k_fill_i32(int32_t* p, uint64_t from, uint64_t to, int32_t v) {
+  for (uint64_t i = from + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < to; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_u64(ull* p, uint64_t n, ull v) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+// ---- device-wide exclusive scan of uint64 (three passes; 2048 items per block) used at load and at compaction
+constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ ull block_excl_scan(ull v, ull* total) {  // 256 threads
+  __shared__ ull wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ull x = v;
+  for (int o = 1; o < 32; o <<= 1) { ull y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    ull s = lane < 8 ? wsum[lane] : 0;
+    for (int o = 1; o < 8; o <<= 1) { ull y = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += y; }
+    if (lane < 8) wsum[lane] = s;
+  }
+  __syncthreads();
+  const ull before = warp ? wsum[warp - 1] : 0;
+  *total = wsum[7];
+  __syncthreads();
+  return before + x - v;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const ull* in, uint64_t n, ull* sums) {
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
+  ull s = 0;
+  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += in[base + i];
+  ull total;
+  block_excl_scan(s, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(ull* sums, uint32_t nb, ull* grand_total) {  // one block
+  ull carry = 0;
+  for (uint32_t base = 0; base < nb; base += SCAN_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    ull v = i < nb ? sums[i] : 0, total;
+    ull ex = block_excl_scan(v, &total);
+    if (i < nb) sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const ull* in, uint64_t n, const ull* sums, ull* out) {
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
+  ull v[SCAN_ITEMS], s = 0;
+  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+  ull total;
+  ull run = sums[blockIdx.x] + block_excl_scan(s, &total);
+  for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = run; run += v[i]; }
+}
+
+// -------------------------------------------------------------------------------------------------------------- count
+
+struct Params {
+  int32_t unk_id, unk_code;
+  uint64_t min_freq;
+};
+
+__device__ __forceinline__ int32_t code_to_id(int32_t code, const Params& P) { return (P.unk_id < 0 && code == P.unk_code) ? P.unk_id : code; }
+
+// bpe.cpp:197-214: every adjacent pair without unk adds the word's count; first sighting = flat position
+__global__ void __launch_bounds__(256) k_count(const int32_t* __restrict__ ids, const ull* __restrict__ woff, const uint32_t* __restrict__ wlen,
+                                               const ull* __restrict__ wcnt, uint32_t n_words, Params P, DeltaTable dt, DevCounters* ctr) {
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += gridDim.x * blockDim.x) {
+    const ull base = woff[wi] + 1;
+    const uint32_t len = wlen[wi];
+    const int64_t c = static_cast<int64_t>(wcnt[wi]);
+    if (len < 2) continue;
+    int32_t a = ids[base];
+    for (uint32_t j = 0; j + 1 < len; j++) {
+      const int32_t b = ids[base + j + 1];
+      if (a != P.unk_code && b != P.unk_code) dt_add(dt, ctr, fc_key(a, b), c, base + j);
+      a = b;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------- merge
+
+// HBM-bound scan: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs that start in it.  A match
+// whose word has no earlier match is the word's leader and goes to the worklist (position of the word's first symbol).
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_detect(const int4* __restrict__ ids4, uint32_t n4, int32_t A, int32_t B, uint32_t* __restrict__ wl, DevCounters* ctr) {
+  const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  constexpr uint32_t CHUNK = 32u * UNROLL;
+  for (uint64_t base = static_cast<uint64_t>(warp) * CHUNK; base < n4; base += static_cast<uint64_t>(n_warps) * CHUNK) {
+    int4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const uint64_t i = base + u * 32u + lane;
+      v[u] = i < n4 ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+    }
+    // first symbol after this chunk (needed by lane 31 of the last row)
+    int32_t after = DEAD;
+    if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldg(ids + 4 * i); }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
+      const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
+      if (lane == 31) nxt = row_next;
+      uint32_t m = 0;
+      m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
+      m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
+      m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
+      m |= (v[u].w == A && nxt == B) ? 8u : 0u;
+      if (__any_sync(0xFFFFFFFFu, m != 0)) {
+        const uint64_t p0 = (base + u * 32u + lane) * 4u;
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          // leader test: walk left to the word header; an earlier (A,B) in the same word disqualifies this match
+          uint64_t q = p0 + k;
+          bool leader = true;
+          for (;;) {
+            const int32_t x = ids[q - 1];
+            if (x < 0) break;
+            if (x == A && ids[q] == B) { leader = false; break; }
+            --q;
+          }
+          if (leader) { const uint32_t idx = atomicAdd(&ctr->wl_n, 1u); wl[idx] = static_cast<uint32_t>(q); }
+        }
+      }
+    }
+  }
+}
+
+// One thread per matched word: the reference's left-to-right rewrite (bpe.cpp:268-296), in place, left-packed.
+__global__ void __launch_bounds__(128) k_apply(int32_t* ids, const ull* __restrict__ wcnt, uint32_t* wlen, const uint32_t* __restrict__ wl,
+                                               int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, DevCounters* ctr) {
+  const uint32_t n = ctr->wl_n;
+  uint32_t my_occ = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t q = wl[i];
+    const uint32_t wi = static_cast<uint32_t>(ids[q - 1]) & ~HDR_BIT;
+    const int64_t c = static_cast<int64_t>(wcnt[wi]);
+    uint64_t r = q, w = q;
+    int32_t cur = ids[r];
+    int32_t prev_id = 0; bool have_prev = false;
+    while (cur >= 0) {
+      const int32_t nxt = ids[r + 1];
+      if (cur == A && nxt == B) {
+        ++my_occ;
+        const uint64_t seq = r * 4ull;
+        if (have_prev) {  // left neighbour = current id there (N if just merged), bpe.cpp:274-281
+          dt_add(dt, ctr, fc_key(prev_id, A), -c, seq + 0);
+          dt_add(dt, ctr, fc_key(prev_id, N), c, seq + 1);
+        }
+        const int32_t nn = ids[r + 2];
+        if (nn >= 0) {  // right neighbour = raw next-next id, bpe.cpp:282-290
+          const int32_t rid = code_to_id(nn, P);
+          dt_add(dt, ctr, fc_key(B, rid), -c, seq + 2);
+          dt_add(dt, ctr, fc_key(N, rid), c, seq + 3);
+        }
+        ids[w] = N;
+        prev_id = N; have_prev = true;
+        ++w; r += 2;
+        cur = nn;
+      } else {
+        if (w != r) ids[w] = cur;
+        prev_id = code_to_id(cur, P); have_prev = true;
+        ++w; ++r;
+        cur = nxt;
+      }
+    }
+    for (uint64_t k = w; k < r; k++) ids[k] = DEAD;
+    wlen[wi] = static_cast<uint32_t>(w - q);
+  }
+  for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
+  if ((threadIdx.x & 31) == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
+}
+
+// Aggregated deltas -> pair table (bpe.cpp:297-313, order-free part) + records for the host.  COUNT=true is the
+// bigram-count flavour (bpe.cpp:219-227): no self/phantom handling, PUSH records only.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
+                                                  int32_t A, int32_t B, Params P, uint64_t flag_value) {
+  const uint32_t n = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
+  if (!COUNT && blockIdx.x == 0 && threadIdx.x == 0) {  // bpe.cpp:315: the merged pair's frequency becomes 0
+    const uint64_t s = pt_slot(pt, ctr, fc_key(A, B));
+    pt.freq[s] = 0ull;
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t ds = dt.list[i];
+    const uint64_t key = dt.keys[ds];
+    const int64_t d = static_cast<int64_t>(dt.delta[ds]);
+    const uint64_t seq = dt.seq[ds];
+    dt.keys[ds] = dt.empty; dt.delta[ds] = 0ull; dt.seq[ds] = SEQ_MAX;
+    const int32_t pa = static_cast<int32_t>(key >> 32), pb = static_cast<int32_t>(key & 0xFFFFFFFFu);  // bpe.cpp:301
+    Rec out; out.key = key; out.seq = seq; out.pad = 0;
+    bool emit = false;
+    if (!COUNT && pa == A && pb == B) continue;  // bpe.cpp:302
+    if (!COUNT && (pa == P.unk_id || pb == P.unk_id)) {  // phantom pair: tracked by the host (Appendix A12)
+      out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d); emit = true;
+    } else {
+      const uint64_t s = pt_slot(pt, ctr, key);
+      const uint64_t old = pt.freq[s];
+      uint64_t nf;
+      if (d < 0) { const uint64_t ad = static_cast<uint64_t>(-d); nf = old >= ad ? old - ad : 0; } else nf = old + static_cast<uint64_t>(d);  // bpe.cpp:303-307
+      pt.freq[s] = nf;
+      if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
+      else if (!COUNT && old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
+    }
+    if (emit) {
+      const uint32_t idx = atomicAdd(&ctr->rec_n, 1u);
+      if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
+    }
+  }
+  // last block publishes the counters to the host and re-arms them for the next pass
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    ctrl->n_recs = ctr->rec_n < rec_cap ? ctr->rec_n : rec_cap;
+    ctrl->occ = ctr->occ;
+    ctrl->pt_n = ctr->pt_n;
+    ctrl->n_leaders = ctr->wl_n;
+    ctrl->n_keys = ctr->dt_n;
+    ctrl->err = ctr->err;
+    ctr->wl_n = 0; ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->occ = 0ull;
+    __threadfence_system();
+    ctrl->flag = flag_value;
+  }
+}
+
+__global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {
+  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < oldt.cap; s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t k = oldt.keys[s];
+    if (k == PT_EMPTY) continue;
+    uint64_t slot = mix64(k) & newt.mask;
+    for (;;) {
+      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&newt.keys[slot]), static_cast<ull>(PT_EMPTY), static_cast<ull>(k));
+      if (prev == PT_EMPTY) { newt.freq[slot] = oldt.freq[s]; break; }
+      slot = (slot + 1) & newt.mask;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ compaction / save
+
+__global__ void k_len1(const uint32_t* wlen, uint32_t n, ull* len1) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) len1[i] = static_cast<ull>(wlen[i]) + 1ull;
+}
+__global__ void k_compact(const int32_t* __restrict__ src, const ull* __restrict__ old_off, const ull* __restrict__ new_off, const uint32_t* __restrict__ wlen,
+                          uint32_t n, int32_t* dst) {
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
+    const ull so = old_off[wi], d = new_off[wi];
+    const uint32_t len = wlen[wi];
+    for (uint32_t j = 0; j <= len; j++) dst[d + j] = src[so + j];
+  }
+}
+__global__ void k_token_freq(const int32_t* __restrict__ ids, const ull* __restrict__ woff, const uint32_t* __restrict__ wlen, const ull* __restrict__ wcnt,
+                             uint32_t n, Params P, ull* freq, uint64_t T) {
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
+    const ull base = woff[wi] + 1, c = wcnt[wi];
+    const uint32_t len = wlen[wi];
+    for (uint32_t j = 0; j < len; j++) {
+      const int32_t id = code_to_id(ids[base + j], P);
+      if (id >= 0 && static_cast<uint64_t>(id) < T) atomicAdd(&freq[id], c);  // bpe.cpp:413
+    }
+  }
+}
+
+// ============================================================================================================ engine
+
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+class CudaEngine : public Engine {
+ public:
+  CudaEngine(int dev, const cudaDeviceProp& prop) : dev_(dev), n_sm_(prop.multiProcessorCount > 0 ? prop.multiProcessorCount : N_SM_FALLBACK) {
+    std::snprintf(name_, sizeof name_, "%s sm_%d%d %d SMs", prop.name, prop.major, prop.minor, n_sm_);
+  }
+  ~CudaEngine() override { release_all(); }
+
+  int init() {
+    CK(cudaSetDevice(dev_));
+    CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    void* cp = nullptr;
+    CK(cudaHostAlloc(&cp, sizeof(Ctrl), cudaHostAllocMapped));
+    std::memset(cp, 0, sizeof(Ctrl));
+    ctrl_ = static_cast<volatile Ctrl*>(cp);
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters)));
+    CK(cudaMemset(ctr_, 0, sizeof(DevCounters)));
+    CK(cudaEventCreate(&ev0_));
+    CK(cudaEventCreate(&ev1_));
+    const char* e = std::getenv("SHRED_TIMING");
+    timing_every_ = e && *e ? std::atoi(e) : 0;
+    return 0;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------- load
+  int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) override {
+    CK(cudaSetDevice(dev_));
+    cfg_ = cfg;
+    vocab_hint_ = cfg.vocab_size < (1ull << 22) ? cfg.vocab_size : (1ull << 22);
+    P_.unk_id = cfg.unk_id;
+    P_.unk_code = cfg.unk_id >= 0 ? cfg.unk_id : UNK_CODE_NEG;
+    P_.min_freq = cfg.min_freq;
+    release_corpus();
+    std::memset(info, 0, sizeof *info);
+    std::memset(&es_, 0, sizeof es_);
+    // --- corpus bytes to HBM, padded with spaces so token walks and 16-byte loads stay in bounds
+    const uint64_t padded = ((n + 15) & ~15ull) + 64;
+    uint8_t* d_text = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_text), padded));
+    double t0 = now_ms();
+    if (n) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
+    CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
+    CK(cudaStreamSynchronize(st_));
+    es_.h2d_ms += now_ms() - t0; es_.h2d_bytes += n;
+
+    CK(cudaEventRecord(ev0_, st_));
+    int rc = ingest(d_text, n, info);
+    cudaFree(d_text);
+    if (rc != 0) return rc;
+    CK(cudaEventRecord(ev1_, st_));
+    CK(cudaStreamSynchronize(st_));
+    float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
+    es_.ingest_device_ms = ms;
+    es_.ingest_bytes = static_cast<double>(n) + 4.0 * info->n_symbols + 12.0 * info->n_words;
+    return 0;
+  }
+
+  int ingest(const uint8_t* d_text, uint64_t n, LoadInfo* info) {
+    DevCounters zero; std::memset(&zero, 0, sizeof zero);
+    WordTable wt; std::memset(&wt, 0, sizeof wt);
+    uint32_t N = 0; ull n_tokens = 0;
+    uint64_t cap = next_pow2(n / 16 + 1); if (cap < (1u << 16)) cap = 1u << 16;
+    uint32_t seed = 0x5bd1e995u;
+    for (int attempt = 0;; ++attempt) {
+      if (attempt > 8) { std::fprintf(stderr, "[ERROR]\t unique-word table did not converge\n"); return -1; }
+      if (cap > (1ull << 32)) { std::fprintf(stderr, "[ERROR]\t unique-word table too large\n"); return -1; }
+      CK(cudaMalloc(reinterpret_cast<void**>(&wt.tag), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&wt.first), cap * 8));
+      CK(cudaMalloc(reinterpret_cast<void**>(&wt.count), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&wt.len), cap * 4));
+      CK(cudaMalloc(reinterpret_cast<void**>(&wt.bucket), cap * 4));
+      wt.cap = cap; wt.mask = cap - 1;
+      CK(cudaMemsetAsync(wt.tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt.first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt.count, 0, cap * 8, st_));
+      CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
+      if (n) { k_tokenize<<<grid_for((n + 15) / 16, 256), 256, 0, st_>>>(d_text, n, wt, ctr_, seed); launches_++; es_.ingest_launches++; }
+      DevCounters c;
+      CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
+      CK(cudaStreamSynchronize(st_));
+      CK(cudaGetLastError());
+      const bool too_full = static_cast<uint64_t>(c.n_unique) * 2 > cap;
+      if ((c.err & (ERR_WT_FULL | ERR_WT_COLLISION)) || too_full) {
+        cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket);
+        if ((c.err & ERR_WT_FULL) || too_full) cap *= 4;
+        if (c.err & ERR_WT_COLLISION) seed = seed * 2654435761u + 12345u;
+        continue;
+      }
+      N = c.n_unique; n_tokens = c.n_tokens;
+      break;
+    }
+    auto free_wt = [&]() { cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket); };
+    if (N >= 0x7FFFFFF0u) { free_wt(); std::fprintf(stderr, "[ERROR]\t too many unique words\n"); return -1; }
+    n_words_ = N;
+    info->n_words = N; info->n_tokens = n_tokens;
+    // --- reference word order: bucket = djb2 & 4095 ascending, first occurrence ascending inside a bucket
+    uint32_t *u_slot = nullptr, *u_n = nullptr, *bcnt = nullptr, *bstart = nullptr, *cursor = nullptr, *tmp_slot = nullptr, *order_slot = nullptr;
+    ull *tmp_first = nullptr, *d_hist = nullptr, *len1 = nullptr, *sums = nullptr;
+    uint8_t* d_keep = nullptr;
+    const uint64_t Na = N ? N : 1;
+    CK(cudaMalloc(reinterpret_cast<void**>(&u_slot), Na * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&tmp_slot), Na * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&order_slot), Na * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&tmp_first), Na * 8));
+    CK(cudaMalloc(reinterpret_cast<void**>(&len1), Na * 8));
+    CK(cudaMalloc(reinterpret_cast<void**>(&u_n), 4)); CK(cudaMalloc(reinterpret_cast<void**>(&bcnt), 4096 * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&bstart), 4097 * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&cursor), 4096 * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_hist), 256 * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&d_keep), 256));
+    const uint32_t nb_scan = static_cast<uint32_t>((Na + SCAN_TILE - 1) / SCAN_TILE);
+    CK(cudaMalloc(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8));
+    auto free_tmp = [&]() {
+      cudaFree(u_slot); cudaFree(tmp_slot); cudaFree(order_slot); cudaFree(tmp_first); cudaFree(len1); cudaFree(u_n); cudaFree(bcnt);
+      cudaFree(bstart); cudaFree(cursor); cudaFree(d_hist); cudaFree(d_keep); cudaFree(sums);
+    };
+    CK(cudaMemsetAsync(u_n, 0, 4, st_)); CK(cudaMemsetAsync(bcnt, 0, 4096 * 4, st_)); CK(cudaMemsetAsync(cursor, 0, 4096 * 4, st_));
+    CK(cudaMemsetAsync(d_hist, 0, 256 * 8, st_));
+    CK(cudaMalloc(reinterpret_cast<void**>(&wcnt_), Na * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&wlen_), Na * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&woff_[0]), (Na + 1) * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&woff_[1]), (Na + 1) * 8));
+    ull S1 = 0;  // total slots = symbols + headers
+    if (N) {
+      k_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, bcnt);
+      k_scan4096<<<1, 1024, 0, st_>>>(bcnt, bstart);
+      k_scatter<<<grid_for(N, 256), 256, 0, st_>>>(wt, u_slot, N, bstart, cursor, tmp_slot, tmp_first);
+      k_rank<<<grid_for(N, 128), 128, 0, st_>>>(wt, tmp_slot, tmp_first, N, bstart, order_slot);
+      k_hist_words<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, d_hist, wcnt_, wlen_, len1);
+      k_scan_sums<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums);
+      k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(sums, nb_scan, sums + nb_scan);
+      k_scan_apply<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums, woff_[0]);
+      launches_ += 8; es_.ingest_launches += 8;
+      CK(cudaMemcpyAsync(&S1, sums + nb_scan, 8, cudaMemcpyDeviceToHost, st_));
+    }
+    CK(cudaMemcpyAsync(info->hist, d_hist, 256 * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    es_.d2h_bytes += 256 * 8 + 8 + sizeof(DevCounters);
+    charset_keep(info->hist, cfg_.coverage, info->keep, &info->n_distinct, &info->n_keep);
+    info->n_symbols = S1 - N;
+    n_slots_ = S1; n_live_ = S1;
+    if (S1 + 64 >= (1ull << 32)) { free_tmp(); free_wt(); std::fprintf(stderr, "[ERROR]\t corpus needs more than 2^32 symbol slots on one GPU\n"); return -1; }
+    ids_cap_ = ((S1 + 8 + 1023) / 1024) * 1024;
+    CK(cudaMalloc(reinterpret_cast<void**>(&ids_[0]), ids_cap_ * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&ids_[1]), ids_cap_ * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&wl_), ids_cap_ * 4));
+    cur_ = 0;
+    CK(cudaMemcpyAsync(d_keep, info->keep, 256, cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(woff_[0] + N, &S1, 8, cudaMemcpyHostToDevice, st_));
+    if (N) { k_symbolize<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, woff_[0], d_keep, P_.unk_code, ids_[0]); launches_++; es_.ingest_launches++; }
+    k_fill_i32<<<grid_for(ids_cap_ - S1, 256), 256, 0, st_>>>(ids_[0], S1, ids_cap_, DEAD); launches_++; es_.ingest_launches++;
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    free_tmp(); free_wt();
+    // --- pair/delta tables sized for this trainer
+    RC(alloc_tables());
+    loaded_ = true;
+    return 0;
+  }
+
+  int alloc_tables() {
+    if (!dt_.keys) {
+      uint64_t cap = next_pow2(8ull * (256 + vocab_hint_) + 1024); if (cap < (1u << 16)) cap = 1u << 16;
+      RC(alloc_dt(cap));
+    }
+    if (!pt_.keys) RC(alloc_pt(&pt_, 1ull << 20));
+    if (!recs_) {
+      rec_cap_ = dt_.cap;
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped));
+    }
+    return 0;
+  }
+  int alloc_dt(uint64_t cap) {
+    if (dt_.keys) { cudaFree(dt_.keys); cudaFree(dt_.delta); cudaFree(dt_.seq); cudaFree(dt_.list); dt_.keys = nullptr; }
+    CK(cudaMalloc(reinterpret_cast<void**>(&dt_.keys), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&dt_.delta), cap * 8));
+    CK(cudaMalloc(reinterpret_cast<void**>(&dt_.seq), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&dt_.list), cap * 4));
+    dt_.cap = static_cast<uint32_t>(cap); dt_.mask = cap - 1;
+    // a key value no pair can produce: high word >= 2^31 that is neither all-ones nor unk_id
+    uint32_t hi = 0x80000000u; if (static_cast<uint32_t>(cfg_.unk_id) == hi) hi = 0x80000001u;
+    dt_.empty = static_cast<uint64_t>(hi) << 32;
+    k_fill_u64<<<grid_for(cap, 256), 256, 0, st_>>>(reinterpret_cast<ull*>(dt_.keys), cap, dt_.empty);
+    CK(cudaMemsetAsync(dt_.delta, 0, cap * 8, st_)); CK(cudaMemsetAsync(dt_.seq, 0xFF, cap * 8, st_));
+    launches_++;
+    if (recs_ && rec_cap_ < dt_.cap) { cudaFreeHost(recs_); recs_ = nullptr; rec_cap_ = dt_.cap; CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped)); }
+    return 0;
+  }
+  int alloc_pt(PairTable* pt, uint64_t cap) {
+    CK(cudaMalloc(reinterpret_cast<void**>(&pt->keys), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&pt->freq), cap * 8));
+    pt->cap = cap; pt->mask = cap - 1;
+    CK(cudaMemsetAsync(pt->keys, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(pt->freq, 0, cap * 8, st_));
+    return 0;
+  }
+  int grow_pt(uint64_t need_entries) {
+    uint64_t cap = pt_.cap; while (need_entries * 2 > cap) cap *= 2;
+    if (cap == pt_.cap) return 0;
+    PairTable nt; std::memset(&nt, 0, sizeof nt);
+    RC(alloc_pt(&nt, cap));
+    k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
+    CK(cudaStreamSynchronize(st_));
+    cudaFree(pt_.keys); cudaFree(pt_.freq);
+    pt_ = nt;
+    return 0;
+  }
+
+  // --------------------------------------------------------------------------------------------------------- count
+  int count_pairs(const Rec** recs, size_t* n) override {
+    CK(cudaSetDevice(dev_));
+    *recs = recs_; *n = 0;
+    if (!loaded_) return 0;
+    for (int attempt = 0; attempt < 12; ++attempt) {
+      CK(cudaMemsetAsync(pt_.keys, 0xFF, pt_.cap * 8, st_)); CK(cudaMemsetAsync(pt_.freq, 0, pt_.cap * 8, st_));
+      CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
+      pt_n_ = 0;
+      ++flag_;
+      CK(cudaEventRecord(ev0_, st_));
+      if (n_words_) { k_count<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, dt_, ctr_); launches_++; }
+      CK(cudaEventRecord(ev1_, st_));
+      // the finalize pass needs dt_n <= cap/2 and room in the pair table: check before consuming the delta table
+      DevCounters c;
+      CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
+      CK(cudaStreamSynchronize(st_));
+      CK(cudaGetLastError());
+      float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
+      if ((c.err & ERR_DT_FULL) || static_cast<uint64_t>(c.dt_n) * 2 > dt_.cap) {  // enlarge the scratch table, redo (ids untouched)
+        RC(alloc_dt(static_cast<uint64_t>(dt_.cap) * 4));
+        continue;
+      }
+      RC(grow_pt(static_cast<uint64_t>(c.dt_n) + 4ull * (256 + vocab_hint_) + 1024));
+      k_finalize<true><<<fin_grid(), 128, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), 0, 0, P_, flag_); launches_++;
+      RC(wait_flag());
+      if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", ctrl_->err); return -1; }
+      es_.count_launches++; es_.count_device_ms += ms; es_.count_bytes += 4.0 * static_cast<double>(n_live_) + 12.0 * n_words_;
+      pt_n_ = ctrl_->pt_n;
+      *n = ctrl_->n_recs;
+      es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
+      return 0;
+    }
+    return -1;
+  }
+
+  // --------------------------------------------------------------------------------------------------------- merge
+  int merge(int32_t a, int32_t b, int32_t new_id, const Rec** recs, size_t* n, uint64_t* occurrences) override {
+    *recs = recs_; *n = 0; *occurrences = 0;
+    // keep the pair table at most half full even if this merge creates every key it can (4 per distinct id)
+    const uint64_t worst_new = 4ull * (static_cast<uint64_t>(new_id) + 2);
+    if ((pt_n_ + worst_new) * 2 > pt_.cap) RC(grow_pt(pt_n_ + worst_new));
+    if (worst_new * 2 > dt_.cap) RC(alloc_dt(next_pow2(worst_new * 2)));
+    // reclaim dead slots once a quarter of the scanned array is dead
+    if (n_slots_ > 4096 && (n_slots_ - n_live_) * 4 > n_slots_) RC(compact());
+    const uint32_t n4 = static_cast<uint32_t>((n_slots_ + 3) / 4);
+    ++flag_;
+    const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
+    if (timed) CK(cudaEventRecord(ev0_, st_));
+    k_detect<4><<<detect_grid(n4), 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_[cur_]), n4, a, b, wl_, ctr_);
+    if (timed) CK(cudaEventRecord(ev1_, st_));
+    k_apply<<<n_sm_ * 2, 128, 0, st_>>>(ids_[cur_], wcnt_, wlen_, wl_, a, b, new_id, P_, dt_, ctr_);
+    k_finalize<false><<<fin_grid(), 128, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), a, b, P_, flag_);
+    launches_ += 3;
+    RC(wait_flag());
+    if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
+    if (timed) {
+      float ms = 0;
+      CK(cudaEventSynchronize(ev1_));
+      cudaEventElapsedTime(&ms, ev0_, ev1_);
+      es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += 4.0 * static_cast<double>(n4) * 4.0;
+    }
+    *n = ctrl_->n_recs; *occurrences = ctrl_->occ;
+    pt_n_ = ctrl_->pt_n;
+    n_live_ -= ctrl_->occ;
+    es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
+    return 0;
+  }
+
+  int compact() {
+    const uint32_t N = n_words_;
+    if (!N) return 0;
+    ull *len1 = nullptr, *sums = nullptr;
+    const uint32_t nb_scan = (N + SCAN_TILE - 1) / SCAN_TILE;
+    CK(cudaMalloc(reinterpret_cast<void**>(&len1), static_cast<uint64_t>(N) * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8));
+    const int nxt = cur_ ^ 1;
+    k_len1<<<grid_for(N, 256), 256, 0, st_>>>(wlen_, N, len1);
+    k_scan_sums<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums);
+    k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(sums, nb_scan, sums + nb_scan);
+    k_scan_apply<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums, woff_[nxt]);
+    ull S1 = 0;
+    CK(cudaMemcpyAsync(&S1, sums + nb_scan, 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaMemcpyAsync(woff_[nxt] + N, &S1, 8, cudaMemcpyHostToDevice, st_));
+    k_compact<<<grid_for(N, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], woff_[nxt], wlen_, N, ids_[nxt]);
+    const uint64_t pad_to = ((S1 + 8 + 1023) / 1024) * 1024;
+    k_fill_i32<<<grid_for(pad_to - S1, 256), 256, 0, st_>>>(ids_[nxt], S1, pad_to < ids_cap_ ? pad_to : ids_cap_, DEAD);
+    launches_ += 6;
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    cudaFree(len1); cudaFree(sums);
+    cur_ = nxt; n_slots_ = S1; n_live_ = S1;
+    es_.compactions++;
+    return 0;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------- save
+  int token_freqs(uint64_t* freq, size_t T) override {
+    CK(cudaSetDevice(dev_));
+    if (!loaded_ || !n_words_ || !T) return 0;
+    ull* d = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&d), T * 8));
+    CK(cudaMemsetAsync(d, 0, T * 8, st_));
+    k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, d, T); launches_++;
+    CK(cudaMemcpyAsync(freq, d, T * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    cudaFree(d);
+    es_.d2h_bytes += T * 8;
+    return 0;
+  }
+  int word_counts(uint64_t* out) override {
+    if (!n_words_) return 0;
+    CK(cudaMemcpyAsync(out, wcnt_, static_cast<uint64_t>(n_words_) * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    es_.d2h_bytes += static_cast<uint64_t>(n_words_) * 8;
+    return 0;
+  }
+  int get_words(uint64_t* counts, uint64_t* off, int32_t* ids, uint64_t ids_cap) override {
+    if (!loaded_) return -1;
+    CK(cudaStreamSynchronize(st_));
+    const uint32_t N = n_words_;
+    std::vector<ull> ho(N + 1); std::vector<uint32_t> hl(N ? N : 1); std::vector<int32_t> hi(n_slots_ ? n_slots_ : 1);
+    if (N) {
+      CK(cudaMemcpy(ho.data(), woff_[cur_], (static_cast<uint64_t>(N) + 1) * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hl.data(), wlen_, static_cast<uint64_t>(N) * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hi.data(), ids_[cur_], n_slots_ * 4, cudaMemcpyDeviceToHost));
+      if (counts) CK(cudaMemcpy(counts, wcnt_, static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost));
+    }
+    uint64_t at = 0;
+    for (uint32_t wi = 0; wi < N; wi++) {
+      if (off) off[wi] = at;
+      if (static_cast<uint32_t>(hi[ho[wi]]) != (HDR_BIT | wi)) return -2;  // layout invariant
+      for (uint32_t j = 0; j < hl[wi]; j++) {
+        int32_t code = hi[ho[wi] + 1 + j];
+        if (ids && at < ids_cap) ids[at] = (cfg_.unk_id < 0 && code == UNK_CODE_NEG) ? cfg_.unk_id : code;
+        at++;
+      }
+    }
+    if (off) off[N] = at;
+    return 0;
+  }
+  uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) override {
+    if (!pt_.keys) return 0;
+    std::vector<uint64_t> k(pt_.cap), f(pt_.cap);
+    if (cudaMemcpy(k.data(), pt_.keys, pt_.cap * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (cudaMemcpy(f.data(), pt_.freq, pt_.cap * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    uint64_t n = 0;
+    for (uint64_t s = 0; s < pt_.cap; s++) if (k[s] != PT_EMPTY) {
+      if (n < cap) { ab[2 * n] = static_cast<int32_t>(k[s] >> 32); ab[2 * n + 1] = static_cast<int32_t>(k[s] & 0xFFFFFFFFu); freq[n] = f[s]; }
+      n++;
+    }
+    return n;
+  }
+  void stats(EngineStats* out) override {
+    *out = es_;
+    out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
+    out->kernel_launches = launches_; out->wait_ms = wait_ms_;
+  }
+  const char* name() override { return name_; }
+
+ private:
+  int grid_for(uint64_t n, int block) const {
+    uint64_t g = (n + block - 1) / block, maxg = static_cast<uint64_t>(n_sm_) * 16;
+    if (g < 1) g = 1;
+    return static_cast<int>(g < maxg ? g : maxg);
+  }
+  int detect_grid(uint32_t n4) const {  // a multiple of the SM count, 8 CTAs of 256 threads per SM at most
+    uint64_t warps_needed = (static_cast<uint64_t>(n4) + 127) / 128, ctas = (warps_needed + 7) / 8;
+    uint64_t maxg = static_cast<uint64_t>(n_sm_) * 8;
+    if (ctas < 1) ctas = 1;
+    return static_cast<int>(ctas < maxg ? ctas : maxg);
+  }
+  int fin_grid() const { return n_sm_ < 32 ? n_sm_ : 32; }
+
+  int wait_flag() {
+    double t0 = now_ms();
+    uint64_t spins = 0;
+    while (__atomic_load_n(&ctrl_->flag, __ATOMIC_ACQUIRE) != flag_) {
+      if ((++spins & 0x3FFF) == 0) {
+        cudaError_t q = cudaStreamQuery(st_);
+        if (q == cudaSuccess) { if (__atomic_load_n(&ctrl_->flag, __ATOMIC_ACQUIRE) == flag_) break; std::fprintf(stderr, "[ERROR]\t device pass finished without publishing its result\n"); return -1; }
+        if (q != cudaErrorNotReady) { std::fprintf(stderr, "[ERROR]\t CUDA: %s\n", cudaGetErrorString(q)); return -1; }
+        if (now_ms() - t0 > 120000.0) { std::fprintf(stderr, "[ERROR]\t device pass timed out\n"); return -1; }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    wait_ms_ += now_ms() - t0;
+    return 0;
+  }
+
+  void release_corpus() {
+    for (int i = 0; i < 2; i++) { if (ids_[i]) cudaFree(ids_[i]); ids_[i] = nullptr; if (woff_[i]) cudaFree(woff_[i]); woff_[i] = nullptr; }
+    if (wcnt_) cudaFree(wcnt_); wcnt_ = nullptr;
+    if (wlen_) cudaFree(wlen_); wlen_ = nullptr;
+    if (wl_) cudaFree(wl_); wl_ = nullptr;
+    n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
+  }
+  void release_all() {
+    cudaSetDevice(dev_);
+    release_corpus();
+    if (dt_.keys) { cudaFree(dt_.keys); cudaFree(dt_.delta); cudaFree(dt_.seq); cudaFree(dt_.list); }
+    if (pt_.keys) { cudaFree(pt_.keys); cudaFree(pt_.freq); }
+    if (recs_) cudaFreeHost(recs_);
+    if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
+    if (ctr_) cudaFree(ctr_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (st_) cudaStreamDestroy(st_);
+  }
+
+  int dev_, n_sm_;
+  char name_[320];
+  cudaStream_t st_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  EngineConfig cfg_{};
+  Params P_{};
+  bool loaded_ = false;
+  uint32_t n_words_ = 0;
+  uint64_t n_slots_ = 0, n_live_ = 0, ids_cap_ = 0;
+  int32_t* ids_[2] = {nullptr, nullptr};
+  ull* woff_[2] = {nullptr, nullptr};
+  int cur_ = 0;
+  ull* wcnt_ = nullptr;
+  uint32_t* wlen_ = nullptr;
+  uint32_t* wl_ = nullptr;
+  DeltaTable dt_{};
+  PairTable pt_{};
+  uint64_t pt_n_ = 0;
+  Rec* recs_ = nullptr;
+  uint32_t rec_cap_ = 0;
+  volatile Ctrl* ctrl_ = nullptr;
+  DevCounters* ctr_ = nullptr;
+  uint64_t flag_ = 0;
+  uint64_t vocab_hint_ = 32768;
+  EngineStats es_{};
+  uint64_t launches_ = 0, merge_seq_ = 0;
+  double wait_ms_ = 0;
+  int timing_every_ = 0;
+};
+
+char g_devname[320] = "no CUDA device";
+
+}  // namespace
+
+Engine* make_device_engine() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    std::fprintf(stderr, "[ERROR]\t CUDA: no usable device (%s)\n", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  int dev = 0;
+  if (const char* s = std::getenv("SHRED_DEVICE")) dev = std::atoi(s);
+  else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (dev < 0 || dev >= n) dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return nullptr;
+  if (prop.major != 10) {
+    std::fprintf(stderr, "[ERROR]\t CUDA: device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library carries sm_100a code only\n", dev, prop.name,
+                 prop.major, prop.minor);
+    return nullptr;
+  }
+  CudaEngine* eng = new CudaEngine(dev, prop);
+  if (eng->init() != 0) { delete eng; return nullptr; }
+  std::snprintf(g_devname, sizeof g_devname, "%s", eng->name());
+  return eng;
+}
+
+}  // namespace shred
+
+extern "C" const char* bpe_b200_device_name(void) {
+  static char buf[320];
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return "no CUDA device";
+  int dev = 0; cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return "no CUDA device";
+  std::snprintf(buf, sizeof buf, "%s sm_%d%d %d SMs", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  return buf;
+}

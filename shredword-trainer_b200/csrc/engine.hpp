@@ -29,6 +29,7 @@ struct EngineConfig {
   int32_t unk_id;
   float coverage;     // already normalised
   uint64_t min_freq;  // already normalised
+  uint64_t vocab_size;  // target vocabulary (sizes scratch tables; not a limit)
 };
 
 struct LoadInfo {

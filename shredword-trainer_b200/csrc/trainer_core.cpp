@@ -99,6 +99,7 @@ int TrainerCore::load_buffer(const uint8_t* text, size_t n) {
   double t0 = now_ms();
   EngineConfig ec;
   ec.unk_id = abi_->config.unk_id; ec.coverage = abi_->config.character_coverage; ec.min_freq = abi_->config.min_pair_freq;
+  ec.vocab_size = abi_->config.target_vocab_size;
   if (eng_->load(text, n, ec, &info_) != 0) return -1;
   corpus_bytes_ = n;
   loaded_ = true;

@@ -1,0 +1,4 @@
+"""B200-native drop-in for the BPE half of the `shredword` trainer package (reference shredword/__init__.py)."""
+from .trainer import BPETrainer, UnigramTrainer
+
+__version__ = "0.1.0+b200"

@@ -12,6 +12,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../../include/shred_abi.h"
 #include "../../shredword-trainer_b200/csrc/charset.hpp"
 #include "../../shredword-trainer_b200/csrc/engine.hpp"
 

@@ -1,0 +1,92 @@
+"""CPU: the product's HOST control code (trainer_core.cpp: push ordering, versions, phantom pairs, exact heap replay,
+save) linked against a CPU stand-in of the device engine that returns its records shuffled (tests/hostsim), checked
+against the golden vectors of the unmodified reference and against the oracle's heap array."""
+import ctypes
+import os
+
+import pytest
+
+from cases import GOLDEN, SMALL, case_ids, corpus_bytes
+from hostsim_lib import HS_SO
+from oracle_lib import Oracle, md5
+
+
+class _Cfg(ctypes.Structure):
+    _fields_ = [("vs", ctypes.c_size_t), ("unk", ctypes.c_int32), ("cov", ctypes.c_float), ("mf", ctypes.c_uint64)]
+
+
+class _Pair(ctypes.Structure):
+    _fields_ = [("a", ctypes.c_int32), ("b", ctypes.c_int32)]
+
+
+class _HeapEnt(ctypes.Structure):
+    _fields_ = [("key", _Pair), ("freq", ctypes.c_uint64), ("version", ctypes.c_uint32)]
+
+
+class _Trainer(ctypes.Structure):
+    _fields_ = [("config", _Cfg), ("heap_data", ctypes.POINTER(_HeapEnt)), ("heap_size", ctypes.c_size_t), ("heap_cap", ctypes.c_size_t),
+                ("words", ctypes.c_void_p), ("word_counts", ctypes.POINTER(ctypes.c_uint64)), ("n_words", ctypes.c_size_t),
+                ("bm", ctypes.c_void_p * 2), ("next_token", ctypes.c_size_t), ("num_merges", ctypes.c_size_t), ("merge_ops", ctypes.POINTER(_Pair))]
+
+
+@pytest.fixture(scope="module")
+def hs(native):
+    os.environ["SHRED_QUIET"] = "1"
+    L = ctypes.CDLL(HS_SO)
+    L.create_trainer.argtypes, L.create_trainer.restype = [ctypes.POINTER(_Cfg)], ctypes.POINTER(_Trainer)
+    L.bpe_b200_load_buffer.argtypes, L.bpe_b200_load_buffer.restype = [ctypes.POINTER(_Trainer), ctypes.c_char_p, ctypes.c_size_t], ctypes.c_int
+    for f in ("bpe_init", "bpe_count_bigrams", "bpe_trainer_destroy"):
+        getattr(L, f).argtypes, getattr(L, f).restype = [ctypes.POINTER(_Trainer)], None
+    L.bpe_train.argtypes, L.bpe_train.restype = [ctypes.POINTER(_Trainer)], ctypes.c_int
+    L.bpe_merge_batch.argtypes, L.bpe_merge_batch.restype = [ctypes.POINTER(_Trainer), ctypes.c_int], ctypes.c_int
+    L.bpe_save.argtypes, L.bpe_save.restype = [ctypes.POINTER(_Trainer), ctypes.c_char_p, ctypes.c_char_p], None
+    return L
+
+
+def _merges(t):
+    n = min(t.contents.num_merges, max(t.contents.config.vs, 1))
+    return [(t.contents.merge_ops[i].a, t.contents.merge_ops[i].b, 256 + i) for i in range(n)]
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=case_ids())
+def test_host_logic_matches_reference(case, hs, tmp_path):
+    import struct
+    data = corpus_bytes(case)
+    vs, unk, cov, mf = case["config"]
+    t = hs.create_trainer(ctypes.byref(_Cfg(vs, unk, cov, mf)))
+    assert hs.bpe_b200_load_buffer(t, data, len(data)) == 0
+    assert t.contents.n_words == case["n_words"]
+    assert hs.bpe_train(t) == case["merges"]
+    mb = b"".join(struct.pack("<3i", *m) for m in _merges(t))
+    assert md5(mb) == case["merges_md5"]
+    model, vocab = tmp_path / "m.bin", tmp_path / "v.txt"
+    hs.bpe_save(t, os.fsencode(str(model)), os.fsencode(str(vocab)))
+    assert model.read_bytes() == mb
+    if case["vocab_md5"] is not None:
+        assert md5(vocab.read_bytes()) == case["vocab_md5"]
+    hs.bpe_trainer_destroy(t)
+
+
+@pytest.mark.parametrize("case", [c for c in SMALL if c["name"] in ("kat_py", "kat_cpp", "rnd003", "rnd017", "multi600k_1", "zipf2m_1")], ids=lambda c: c["name"])
+def test_heap_array_identical_stepwise(case, hs):
+    """After bpe_init and after every single merge the replay heap (pairs and frequencies, array order) equals the
+    reference-order heap of the oracle.  Versions may differ (the host bumps them on demotion), so they are not compared."""
+    data = corpus_bytes(case)
+    vs, unk, cov, mf = case["config"]
+    o = Oracle(vs, unk, cov, mf); o.load_bytes(data); o.init()
+    t = hs.create_trainer(ctypes.byref(_Cfg(vs, unk, cov, mf)))
+    hs.bpe_b200_load_buffer(t, data, len(data)); hs.bpe_init(t)
+    steps = 0
+    while True:
+        ho = [(a, b, f) for a, b, f, _ in o.heap()]
+        hh = [(t.contents.heap_data[i].key.a, t.contents.heap_data[i].key.b, t.contents.heap_data[i].freq) for i in range(t.contents.heap_size)]
+        assert hh == ho, f"heap differs after {steps} merges"
+        if steps >= 60 or steps >= vs - 256:
+            break
+        mo, mh = o.merge_batch(1), hs.bpe_merge_batch(t, 1)
+        assert mo == mh
+        if mo <= 0:
+            break
+        steps += 1
+    assert _merges(t) == o.merges()
+    hs.bpe_trainer_destroy(t); o.destroy()
