@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- BPE train() throughput on B200 (BASELINE.json: "BPE train() wall-s & merges/s, 32k vocab ...").
+
+A "step" is one full pass of the hot path over the synthetic corpus: bpe_load_corpus (host buffer -> HBM -> unique-word
+table) + bpe_train (pair count + merge loop) + reading the merge list back.
+  value  merges/s of bpe_train() alone, corpus already resident in HBM, timed with CUDA events on the library's stream
+  e2e    merges/s through the C ABI with HOST buffers: pinned corpus bytes -> load -> train -> merge list on the host
+  roofline      the dominant kernel (k_detect, the per-merge HBM scan): algorithmic bytes / CUDA-event duration
+  cpu_baseline  the unmodified reference (oracle/_ref, pinned with the zero-fill malloc shim) on a bounded sample
+
+python bench.py --gpus N --steps K --warmup W            (N>1 under torch.distributed.run: one rank per GPU)
+python bench.py --impl reference ...                      (times the reference's own CPU implementation)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "shredword-trainer_b200")
+sys.path.insert(0, PKG)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (bytes, seed, w, mode, vocab_size, unk_id, coverage, min_pair_freq)
+    "config0_100MB": (100_000_000, 1, 20, "zipf", 8192, 0, 0.995, 2000),
+    "config1_1GB": (1_000_000_000, 1, 22, "zipf", 32000, 0, 0.995, 2000),
+    "config2_10GB": (10_000_000_000, 1, 24, "zipf", 32000, 0, 0.995, 2000),
+    "config3_multi": (10_000_000_000, 1, 24, "multi", 65536, 0, 0.995, 2),
+    "tiny": (4_000_000, 1, 16, "zipf", 2000, 0, 0.995, 20),
+}
+REF_SAMPLE_BYTES = 16 << 20   # bounded sample for the CPU reference: first 16 MiB of the corpus ...
+REF_SAMPLE_MERGES = 40        # ... and this many merges (the reference needs ~47 min just to load 1 GB)
+
+
+def scratch_dir():
+    for d in ("/dev/shm", "/tmp"):
+        if os.path.isdir(d) and os.access(d, os.W_OK):
+            p = os.path.join(d, "shred_bench")
+            os.makedirs(p, exist_ok=True)
+            return p
+    return ROOT
+
+
+def make_corpus(workload, rank=0):
+    nbytes, seed, w, mode = WORKLOADS[workload][:4]
+    path = os.path.join(scratch_dir(), f"{workload}_s{seed}_w{w}_{mode}.txt")
+    if not os.path.exists(path):
+        tmp = path + f".tmp{rank}"
+        subprocess.run([os.path.join(PKG, "build", "gen_corpus"), tmp, str(nbytes), str(seed), str(w), mode, "16"], check=True, stdout=subprocess.DEVNULL)
+        os.replace(tmp, path)
+    return path
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                 stdout=subprocess.PIPE, text=True)
+        except OSError:
+            return
+        self.proc = p
+        for line in p.stdout:
+            if self.stop_flag:
+                break
+            self.samples.append([x.strip() for x in line.split(",")])
+        p.kill()
+
+    def finish(self):
+        self.stop_flag = True
+        if hasattr(self, "proc"):
+            self.proc.kill()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_sample(corpus_path, cfg, steps=1, warmup=0):
+    """The unmodified reference (oracle/_ref) on a bounded sample of the workload; falls back to the C oracle port."""
+    from oracle_lib import REF_HARNESS, REF_SO, ZMALLOC, have_reference
+    vocab, unk, cov, mf = cfg
+    d = scratch_dir()
+    sample = os.path.join(d, os.path.basename(corpus_path) + ".sample16M")
+    if not os.path.exists(sample):
+        with open(corpus_path, "rb") as f:
+            data = f.read(REF_SAMPLE_BYTES)
+        data = data[: data.rfind(b"\n") + 1] if b"\n" in data else data
+        open(sample, "wb").write(data)
+    nbytes = os.path.getsize(sample)
+    runs = []
+    kind = "reference" if have_reference() else "port"
+    for it in range(warmup + steps):
+        if kind == "reference":
+            js = os.path.join(d, "ref_sample.json")
+            env = dict(os.environ, LD_PRELOAD=ZMALLOC)
+            subprocess.run([REF_HARNESS, REF_SO, sample, str(vocab), str(unk), repr(float(cov)), str(mf), "--max-merges", str(REF_SAMPLE_MERGES), "--json", js],
+                           env=env, check=True, stdout=subprocess.DEVNULL)
+            info = json.load(open(js))
+            load_s, train_s, merges = info["load_s"], info["train_s"], info["merges"]
+        else:
+            from oracle_lib import Oracle
+            o = Oracle(vocab, unk, cov, mf)
+            t0 = time.perf_counter(); o.load_corpus(sample); t1 = time.perf_counter()
+            o.init(); merges = 0
+            while merges < REF_SAMPLE_MERGES and o.merge_batch(1) > 0:
+                merges += 1
+            train_s, load_s = time.perf_counter() - t1, t1 - t0
+            o.destroy()
+        if it >= warmup:
+            runs.append((load_s, train_s, merges))
+    load_s = sum(r[0] for r in runs) / len(runs)
+    train_s = sum(r[1] for r in runs) / len(runs)
+    merges = runs[0][2]
+    return {"value": merges / train_s if train_s > 0 else 0.0, "unit": "merges/s", "cores": 1, "kind": kind,
+            "sample": f"first {nbytes} bytes of the corpus, bpe_init + {merges} merges (train part only; load of the sample took {load_s:.2f} s); "
+                      f"the reference is single-threaded",
+            "load_s": load_s, "train_s": train_s, "merges": merges, "sample_bytes": nbytes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SHRED_BENCH_WORKLOAD", "config1_1GB"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    nbytes, seed, w, mode, vocab, unk, cov, mf = WORKLOADS[args.workload]
+    config = {"workload": f"{args.workload}: synthetic {mode} corpus {nbytes} bytes (gen_corpus seed={seed} w={w}), vocab_size={vocab} unk_id={unk} "
+                          f"character_coverage={cov} min_pair_freq={mf}",
+              "l2": "inputs_exceed_l2" if nbytes > 300_000_000 else "inputs_fit_l2_small_workload",
+              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU, no data-path collective)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        corpus = make_corpus(args.workload)
+        cb = reference_sample(corpus, (vocab, unk, cov, mf), steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "bpe_train_merges_per_s", "value": cb["value"], "unit": "merges/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * (cb["train_s"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["SHRED_QUIET"] = "1"
+    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "4")  # CUDA events around every 4th merge scan
+    os.environ["SHRED_DEVICE"] = str(local_rank)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge._load_build().build()
+    if world > 1:
+        dist.barrier()
+    from shredword import BPETrainer
+
+    corpus = make_corpus(args.workload, rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        corpus = make_corpus(args.workload, rank)
+    # host buffer: pinned memory holding the corpus bytes (the "HOST buffers" of the end-to-end leg)
+    size = os.path.getsize(corpus)
+    host = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+    with open(corpus, "rb") as f:
+        f.readinto(host.numpy())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        t = BPETrainer(vocab, unk, cov, mf)
+        t0 = time.perf_counter()
+        t.load_bytes(host)
+        t1 = time.perf_counter()
+        n = t.train()
+        merges = t.merges()  # merge list read on the host (Trainer.merge_ops mirror)
+        t2 = time.perf_counter()
+        st = t.stats()
+        t.destroy()
+        return n, t1 - t0, t2 - t1, st, merges
+
+    import contextlib
+    import io
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    with quiet:
+        for _ in range(args.warmup):
+            one_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    steps = []
+    with quiet:
+        for _ in range(args.steps):
+            steps.append(one_step())
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.finish()
+
+    merges = steps[0][0]
+    train_dev_ms = sum(s[3]["train_device_ms"] for s in steps)
+    e2e_s = sum(s[1] + s[2] for s in steps)
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([train_dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        train_dev_ms, e2e_s, wall = tt.tolist()
+    total_merges = merges * args.steps * world
+    st = steps[-1][3]
+    scan_ms = sum(s[3]["scan_device_ms"] for s in steps)
+    scan_bytes = sum(s[3]["scan_bytes"] for s in steps)
+    scan_n = sum(s[3]["scan_launches"] for s in steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    line = {
+        "metric": "bpe_train_merges_per_s", "value": total_merges / (train_dev_ms * 1e-3), "unit": "merges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": config, "clocks": clocks,
+        "e2e": {"value": total_merges / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]) + 8 * merges,
+                "load_s_per_step": sum(s[1] for s in steps) / args.steps, "train_s_per_step": sum(s[2] for s in steps) / args.steps},
+        "gpu_launches": int(sum(s[3]["kernel_launches"] for s in steps)),
+        "roofline": {"bound": "hbm", "kernel": "k_detect (per-merge scan of the symbol array)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "launches_timed": int(scan_n), "avg_launch_us": 1e3 * scan_ms / scan_n if scan_n else None,
+                     "bytes_per_launch": scan_bytes / scan_n if scan_n else None},
+        "detail": {"merges_per_step": merges, "n_words": int(st["n_words"]), "n_symbols_initial": int(st["n_symbols_initial"]), "n_symbols_final": int(st["n_symbols_live"]),
+                   "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
+                   "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"],
+                   "ingest_device_ms": st["ingest_device_ms"], "ingest_gbs": st["ingest_bytes"] / (st["ingest_device_ms"] * 1e-3) / 1e9 if st["ingest_device_ms"] else None,
+                   "count_device_ms": st["count_device_ms"], "count_gbs": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 if st["count_device_ms"] else None,
+                   "h2d_ms": st["h2d_ms"], "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
+                   "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = reference_sample(corpus, (vocab, unk, cov, mf))
+            except Exception as e:  # the checker must never take the measurement down
+                line["cpu_baseline"] = {"value": None, "unit": "merges/s", "cores": 1, "kind": "unavailable", "sample": str(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

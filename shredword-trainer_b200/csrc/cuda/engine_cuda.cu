@@ -61,7 +61,7 @@ constexpr uint64_t PT_EMPTY = ~0ull;
 constexpr uint64_t SEQ_MAX = ~0ull;
 constexpr int N_SM_FALLBACK = 148;
 
-enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16 };
+enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ te
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t prev = base ? text[base - 1] : 32u;
+    // a NUL byte hides the rest of its line in the reference (fgets + strlen, bpe.cpp:131-147): report it, the host
+    // blanks the hidden spans and loads again
+    if (((v.x - 0x01010101u) & ~v.x & 0x80808080u) | ((v.y - 0x01010101u) & ~v.y & 0x80808080u) | ((v.z - 0x01010101u) & ~v.z & 0x80808080u) |
+        ((v.w - 0x01010101u) & ~v.w & 0x80808080u))
+      atomicOr(&ctr->err, ERR_HAS_NUL);
     // delimiter mask of my 16 bytes
     uint32_t dm = 0;
 #pragma unroll
@@ -588,6 +593,8 @@ class CudaEngine : public Engine {
     CK(cudaMemset(ctr_, 0, sizeof(DevCounters)));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
+    CK(cudaEventCreate(&evm0_));
+    CK(cudaEventCreate(&evm1_));
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     return 0;
@@ -646,6 +653,10 @@ class CudaEngine : public Engine {
       CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
       CK(cudaStreamSynchronize(st_));
       CK(cudaGetLastError());
+      if (c.err & ERR_HAS_NUL) {
+        cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket);
+        return 1;
+      }
       const bool too_full = static_cast<uint64_t>(c.n_unique) * 2 > cap;
       if ((c.err & (ERR_WT_FULL | ERR_WT_COLLISION)) || too_full) {
         cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket);
@@ -916,6 +927,13 @@ class CudaEngine : public Engine {
     }
     return n;
   }
+  int mark_begin() override { CK(cudaEventRecord(evm0_, st_)); return 0; }
+  double mark_end() override {
+    if (cudaEventRecord(evm1_, st_) != cudaSuccess || cudaEventSynchronize(evm1_) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, evm0_, evm1_) != cudaSuccess) return -1.0;
+    return ms;
+  }
   void stats(EngineStats* out) override {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
@@ -972,13 +990,15 @@ class CudaEngine : public Engine {
     if (ctr_) cudaFree(ctr_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    if (evm0_) cudaEventDestroy(evm0_);
+    if (evm1_) cudaEventDestroy(evm1_);
     if (st_) cudaStreamDestroy(st_);
   }
 
   int dev_, n_sm_;
   char name_[320];
   cudaStream_t st_ = nullptr;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evm0_ = nullptr, evm1_ = nullptr;
   EngineConfig cfg_{};
   Params P_{};
   bool loaded_ = false;

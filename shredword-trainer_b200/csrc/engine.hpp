@@ -53,7 +53,8 @@ class Engine {
  public:
   virtual ~Engine() {}
   // Tokenise `text`, build the unique-word table in reference order, apply character coverage, lay the symbols out.
-  // A second load replaces the first.  Returns 0 or -1.
+  // A second load replaces the first.  Returns 0, -1 on failure, or 1 if the text contains NUL bytes (nothing is
+  // loaded then: the caller blanks the spans the reference would not see and calls load again).
   virtual int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) = 0;
   // Reset the pair table, count all adjacent non-unk pairs; *recs = PUSH records for entries with freq >= min.
   virtual int count_pairs(const Rec** recs, size_t* n) = 0;
@@ -66,6 +67,9 @@ class Engine {
   virtual int get_words(uint64_t* counts, uint64_t* off, int32_t* ids, uint64_t ids_cap) = 0;
   virtual uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) = 0;
   virtual void stats(EngineStats* out) = 0;
+  // device-side stopwatch on the engine's stream (CUDA events): mark_begin(), ..., mark_end() -> elapsed ms
+  virtual int mark_begin() = 0;
+  virtual double mark_end() = 0;
   virtual const char* name() = 0;
 };
 

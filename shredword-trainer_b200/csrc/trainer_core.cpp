@@ -95,12 +95,42 @@ int TrainerCore::load_file(const char* path) {
   return rc;
 }
 
+// The reference reads the file with fgets into a growing buffer and measures each line with strlen
+// (bpe.cpp:129-147), so a NUL byte hides the rest of its fgets chunk.  This replays that loop over the in-memory
+// image and blanks every byte the reference would not see; the result has no NUL and tokenises identically.
+static std::vector<uint8_t> blank_hidden_spans(const uint8_t* text, size_t n) {
+  std::vector<uint8_t> out(n, static_cast<uint8_t>(' '));
+  size_t cap = 4096, pos = 0;  // bpe.cpp:123,129
+  while (pos < n) {
+    const size_t start = pos;
+    size_t raw = 0;
+    while (raw < cap - 1 && pos < n) { uint8_t c = text[pos++]; raw++; if (c == '\n') break; }  // fgets(line, cap)
+    const void* z = std::memchr(text + start, 0, raw);
+    size_t len = z ? static_cast<size_t>(static_cast<const uint8_t*>(z) - (text + start)) : raw;  // strlen
+    while (len == cap - 1 && text[start + len - 1] != '\n') {  // bpe.cpp:133-145
+      cap *= 2;
+      if (pos >= n) break;
+      size_t room = cap - len, got = 0;
+      while (got < room - 1 && pos < n) { uint8_t c = text[pos++]; got++; if (c == '\n') break; }
+      const void* z2 = std::memchr(text + start + len, 0, got);
+      len = z2 ? static_cast<size_t>(static_cast<const uint8_t*>(z2) - (text + start)) : len + got;
+    }
+    std::memcpy(out.data() + start, text + start, len);
+  }
+  return out;
+}
+
 int TrainerCore::load_buffer(const uint8_t* text, size_t n) {
   double t0 = now_ms();
   EngineConfig ec;
   ec.unk_id = abi_->config.unk_id; ec.coverage = abi_->config.character_coverage; ec.min_freq = abi_->config.min_pair_freq;
   ec.vocab_size = abi_->config.target_vocab_size;
-  if (eng_->load(text, n, ec, &info_) != 0) return -1;
+  int rc = eng_->load(text, n, ec, &info_);
+  if (rc == 1) {  // NUL bytes present
+    std::vector<uint8_t> visible = blank_hidden_spans(text, n);
+    rc = eng_->load(visible.data(), n, ec, &info_);
+  }
+  if (rc != 0) return -1;
   corpus_bytes_ = n;
   loaded_ = true;
   // host mirrors of Corpus (bpe.h:37-41): counts are real, words[] are non-NULL placeholders (symbols live in HBM)
@@ -225,6 +255,7 @@ int TrainerCore::merge_batch(int batch_size) {
 
 int TrainerCore::train() {  // bpe.cpp:345-386
   double t0 = now_ms();
+  eng_->mark_begin();
   host_heap_ms_ = 0; occurrences_ = 0;
   heap_.pushes = heap_.pops = 0;
   if (!quiet_) std::printf("[INFO]\t Starting BPE training (target vocab size: %zu)\n", abi_->config.target_vocab_size);
@@ -240,6 +271,7 @@ int TrainerCore::train() {  // bpe.cpp:345-386
     if (merged <= 0) { if (!quiet_) std::printf("[WARNING]\t No merges performed, stopping\n"); break; }
     total += merged;
   }
+  train_device_ms_ = eng_->mark_end();
   train_wall_ms_ = now_ms() - t0;
   merges_last_ = static_cast<uint64_t>(total);
   if (!quiet_) std::printf("[INFO]\t Training completed. Performed %d merges\n", total);
@@ -297,7 +329,7 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->count_launches = es.count_launches; s->count_device_ms = es.count_device_ms; s->count_bytes = es.count_bytes;
   s->ingest_launches = es.ingest_launches; s->ingest_device_ms = es.ingest_device_ms; s->ingest_bytes = es.ingest_bytes;
   s->kernel_launches = es.kernel_launches;
-  s->load_wall_ms = load_wall_ms_; s->h2d_ms = es.h2d_ms; s->train_wall_ms = train_wall_ms_; s->host_heap_ms = host_heap_ms_;
+  s->load_wall_ms = load_wall_ms_; s->h2d_ms = es.h2d_ms; s->train_wall_ms = train_wall_ms_; s->train_device_ms = train_device_ms_; s->host_heap_ms = host_heap_ms_;
   s->wait_ms = es.wait_ms; s->save_wall_ms = save_wall_ms_;
   s->h2d_bytes = es.h2d_bytes; s->d2h_bytes = es.d2h_bytes;
 }

@@ -47,7 +47,7 @@ class TrainerCore {
   Symbol placeholder_;
   // statistics of the last load/train
   uint64_t occurrences_ = 0, merges_last_ = 0, corpus_bytes_ = 0;
-  double load_wall_ms_ = 0, train_wall_ms_ = 0, host_heap_ms_ = 0, save_wall_ms_ = 0;
+  double load_wall_ms_ = 0, train_wall_ms_ = 0, train_device_ms_ = 0, host_heap_ms_ = 0, save_wall_ms_ = 0;
   bool log_merges_ = false, quiet_ = false;
 };
 

@@ -26,6 +26,7 @@ class HostSimEngine : public Engine {
  public:
   int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) override {
     cfg_ = cfg;
+    if (n && std::memchr(text, 0, n)) return 1;
     std::unordered_map<std::string, size_t> idx;
     struct W { std::string s; uint64_t count; uint32_t bucket; size_t first; };
     std::vector<W> ws;
@@ -148,6 +149,8 @@ class HostSimEngine : public Engine {
     return i;
   }
   void stats(EngineStats* out) override { std::memset(out, 0, sizeof *out); out->pair_entries = table_.size(); }
+  int mark_begin() override { return 0; }
+  double mark_end() override { return 0.0; }
   const char* name() override { return "hostsim (CPU stand-in, tests only)"; }
 
  private:

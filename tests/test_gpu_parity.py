@@ -1,0 +1,229 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes mirror shredword-trainer_b200/shredword), against
+the CPU oracle on the same inputs and against the golden vectors of the unmodified reference.  Staged so that a
+failure names the first stage that diverges: ingest -> charset -> pair count + initial heap -> single merges -> full
+train -> saved files."""
+import os
+import struct
+import subprocess
+
+import pytest
+
+from cases import GOLDEN, SMALL, case_ids, corpus_bytes
+from corpora import generated_corpus
+from oracle_lib import Oracle, md5
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T(native):
+    os.environ["SHRED_QUIET"] = "1"
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from shredword import BPETrainer
+    return BPETrainer
+
+
+def _merge_bytes(merges):
+    return b"".join(struct.pack("<3i", *m) for m in merges)
+
+
+STAGED = [c for c in SMALL if c["name"] in ("kat_py", "kat_cpp", "kat_py_unk-1", "rnd003", "rnd005", "rnd017", "rnd023", "rnd031", "rnd044",
+                                             "multi600k_0", "multi600k_1", "multi600k_2", "multi600k_3", "zipf2m_0", "zipf2m_1", "zipf2m_3")]
+
+
+@pytest.mark.parametrize("case", STAGED, ids=lambda c: c["name"])
+def test_ingest_matches_oracle(case, T):
+    """unique words in reference order, their counts, ids after unk substitution, histogram and keep mask"""
+    data = corpus_bytes(case)
+    vs, unk, cov, mf = case["config"]
+    o = Oracle(vs, unk, cov, mf); o.load_bytes(data)
+    t = T(vs, unk, cov, mf); t.load_bytes(data)
+    assert t.num_words == o.num_words == case["n_words"]
+    keep, hist = t.charset()
+    okeep, ohist = o.keep_mask()
+    assert hist == ohist
+    assert keep == okeep
+    gw = t.words()
+    for i, (ids, cnt) in enumerate(gw):
+        assert cnt == o.L.oracle_word_count(o.h, i), f"count of word {i}"
+        assert ids == o.word_ids(i), f"symbols of word {i}"
+    st = t.stats()
+    assert st["n_symbols_initial"] == o.num_symbols
+    t.destroy(); o.destroy()
+
+
+@pytest.mark.parametrize("case", STAGED, ids=lambda c: c["name"])
+def test_count_and_stepwise_merges_match_oracle(case, T):
+    """pair table after bpe_init, the replay heap (array order) after init and after each of the first merges"""
+    data = corpus_bytes(case)
+    vs, unk, cov, mf = case["config"]
+    o = Oracle(vs, unk, cov, mf); o.load_bytes(data); o.init()
+    t = T(vs, unk, cov, mf); t.load_bytes(data); t.init()
+    gp = {k: v for k, v in t.pairs().items() if v}
+    op = {k: v for k, v in o.pairs().items() if v}
+    assert gp == op
+    steps = 0
+    while True:
+        assert [(a, b, f) for a, b, f, _ in t.heap()] == [(a, b, f) for a, b, f, _ in o.heap()], f"heap differs after {steps} merges"
+        if steps >= 40 or steps >= vs - 256:
+            break
+        mo, mg = o.merge_batch(1), t.merge_batch(1)
+        assert mo == mg
+        if mo <= 0:
+            break
+        steps += 1
+        assert t.merges()[-1] == o.merges()[-1], f"merge {steps}"
+    # word table after the merges
+    gw = t.words()
+    for i in (0, len(gw) // 2, len(gw) - 1) if gw else ():
+        assert gw[i][0] == o.word_ids(i)
+    gp = {k: v for k, v in t.pairs().items() if v and unk not in k}
+    op = {k: v for k, v in o.pairs().items() if v and unk not in k}
+    assert gp == op
+    t.destroy(); o.destroy()
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=case_ids())
+def test_train_matches_reference_golden(case, T, tmp_path):
+    """full train + save, bit-exact against the unmodified reference's merge list and vocab file"""
+    data = corpus_bytes(case)
+    vs, unk, cov, mf = case["config"]
+    t = T(vs, unk, cov, mf)
+    t.load_bytes(data)
+    assert t.num_words == case["n_words"]
+    assert t.train() == case["merges"]
+    mb = _merge_bytes(t.merges())
+    assert md5(mb) == case["merges_md5"]
+    model, vocab = tmp_path / "m.bin", tmp_path / "v.txt"
+    t.save(str(model), str(vocab))
+    assert model.read_bytes() == mb
+    if case["vocab_md5"] is not None:
+        assert md5(vocab.read_bytes()) == case["vocab_md5"]
+    t.destroy()
+
+
+def test_load_from_file_and_compaction(T, tmp_path):
+    """bpe_load_corpus (file path) on a corpus large enough that dead slots get compacted during training"""
+    p = generated_corpus(str(tmp_path / "z.txt"), 3_000_000, 11, 14, "zipf")
+    o = Oracle(4000, 0, 0.995, 2); o.load_corpus(p); n = o.train()
+    t = T(4000, 0, 0.995, 2); t.load_corpus(p)
+    assert t.train() == n
+    assert t.merges() == o.merges()
+    st = t.stats()
+    assert st["compactions"] >= 1
+    assert st["n_symbols_live"] == o.num_symbols
+    for i, (ids, cnt) in enumerate(t.words()[:2000]):
+        assert ids == o.word_ids(i)
+    mo, vo, mg, vg = (str(tmp_path / x) for x in ("mo", "vo", "mg", "vg"))
+    o.save(mo, vo); t.save(mg, vg)
+    assert open(mo, "rb").read() == open(mg, "rb").read() and open(vo, "rb").read() == open(vg, "rb").read()
+    t.destroy(); o.destroy()
+
+
+EDGE = {
+    "empty": b"",
+    "only_delims": b" \n\t\r\n   ",
+    "single_token": b"a",
+    "single_pair": b"ab",
+    "no_final_newline": b"abc abc abd abd abc",
+    "repeated_char_runs": b"aaaaaaa aaaa aaa aa a aaaaaaaaaaaaaaaa bbbbaaaabbbb\n" * 7,
+    "long_word": (b"xy" * 6000) + b" " + (b"xyz" * 3000) + b"\n" + b"xy xyz xyxy\n" * 20,
+    "long_line": b" ".join([b"tok%d" % (i % 37) for i in range(20000)]),
+    "nul_bytes": b"abc abd\x00hidden hidden hidden\nabc abd abc\x00\x00 zz\nplain line abc\n" * 9,
+    "high_bytes": bytes(range(128, 256)) * 3 + b" " + bytes(range(128, 256)) + b"\n",
+    "tabs_crlf": b"one\ttwo\r\nthree  two\tone\r\n" * 30,
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE), ids=sorted(EDGE))
+@pytest.mark.parametrize("cfg", [(400, 0, 0.995, 1), (300, -1, 0.9, 2)], ids=["unk0", "unk-1"])
+def test_edge_cases_match_oracle(name, cfg, T, tmp_path):
+    data = EDGE[name]
+    o = Oracle(*cfg); o.load_bytes(data); n = o.train()
+    t = T(*cfg); t.load_bytes(data)
+    assert t.num_words == o.num_words
+    assert t.train() == n
+    assert t.merges() == o.merges()
+    mo, vo, mg, vg = (str(tmp_path / x) for x in ("mo", "vo", "mg", "vg"))
+    o.save(mo, vo); t.save(mg, vg)
+    assert open(mo, "rb").read() == open(mg, "rb").read() and open(vo, "rb").read() == open(vg, "rb").read()
+    t.destroy(); o.destroy()
+
+
+def test_call_order_semantics(T, tmp_path):
+    a, b = b"aa bb aa cc aa\n" * 50, b"xyz xyz xy zz\n" * 50
+    # second load replaces the first (reference bpe.cpp:176-183)
+    t = T(300, 0, 0.995, 1); t.load_bytes(a); t.load_bytes(b); t.train()
+    o = Oracle(300, 0, 0.995, 1); o.load_bytes(b); o.train()
+    assert t.merges() == o.merges()
+    # train twice keeps merging from the merged corpus (reference bpe.cpp:351)
+    data = corpus_bytes([c for c in GOLDEN if c["name"] == "kat_py"][0])
+    t2 = T(280, 0, 0.995, 2); t2.load_bytes(data); n1 = t2.train(); n2 = t2.train()
+    o2 = Oracle(280, 0, 0.995, 2); o2.load_bytes(data); assert (o2.train(), o2.train()) == (n1, n2)
+    assert t2.num_merges == o2.num_merges and t2.merges() == o2.merges()
+    # vocab_size < 256 -> 0 merges (reference test_bpe.py:56-65); destroy without load; missing file -> IOError
+    t3 = T(50, 0, 0.995, 1000); t3.load_bytes(data); assert t3.train() == 0; t3.destroy()
+    t4 = T(10); 
+    with pytest.raises(IOError):
+        t4.load_corpus(str(tmp_path / "missing.txt"))
+    t4.destroy()
+    # bpe_count_bigrams directly after load seeds the heap (reference bpe_test.cpp:133-167)
+    t5 = T(300, -1, 0.99, 2); t5.load_bytes(open(os.path.join(os.path.dirname(__file__), "golden", "kat_cpp.txt"), "rb").read())
+    t5.count_bigrams()
+    h = t5.heap()
+    assert len(h) > 0 and h[0][2] >= h[1][2]
+    assert t5.merge_batch(1) == 1 and t5.num_merges == 1
+    for x in (t, t2, t5):
+        x.destroy()
+    o.destroy(); o2.destroy()
+
+
+def test_reference_pytest_contract(T, tmp_path):
+    """the three checks of the reference's own test/test_bpe.py, through the same Python API"""
+    corpus = os.path.join(os.path.dirname(__file__), "golden", "kat_py.txt")
+    t = T(vocab_size=300, min_pair_freq=2)
+    t.load_corpus(corpus)
+    assert t.train() > 0
+    model, vocab = tmp_path / "out" / "bpe.model", tmp_path / "out" / "bpe.vocab"
+    t.save(str(model), str(vocab)); t.destroy()
+    assert model.stat().st_size > 0 and vocab.stat().st_size > 0
+    assert model.stat().st_size == 44 * 12 and vocab.read_bytes().count(b"\n") == 256 + 44 + 1
+
+
+def test_cli_drop_in(native, tmp_path):
+    """trainer.exe key=value CLI (reference trainer.cpp): unk_id is fixed to -1, files equal the reference's"""
+    corpus = os.path.join(os.path.dirname(__file__), "golden", "kat_cpp.txt")
+    model, vocab = tmp_path / "m.bin", tmp_path / "v.txt"
+    r = subprocess.run([native["exe"], f"input={corpus}", "model_type=bpe", f"output_model={model}", f"output_vocab={vocab}", "vocab_size=300",
+                        "character_coverage=0.99", "min_pair_freq=2", "bogus", "other=1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = [c for c in GOLDEN if c["name"] == "kat_cpp"][0]
+    assert md5(model.read_bytes()) == g["merges_md5"] and md5(vocab.read_bytes()) == g["vocab_md5"]
+    assert subprocess.run([native["exe"]], capture_output=True).returncode == 0
+    assert subprocess.run([native["exe"], "input=x"], capture_output=True).returncode == 1
+    assert subprocess.run([native["exe"], f"input={corpus}", "model_type=unigram", "output_model=a", "output_vocab=b"], capture_output=True).returncode == 1
+
+
+def test_size_independent_properties_at_scale(T, tmp_path):
+    """100 MB (BASELINE config 1 shape): properties that hold at any size + the oracle's full answer"""
+    p = generated_corpus(str(tmp_path / "c1.txt"), 100_000_000, 1, 20, "zipf")
+    t = T(8192, 0, 0.995, 2000); t.load_corpus(p)
+    st0 = t.stats()
+    n = t.train()
+    st = t.stats()
+    merges = t.merges()
+    assert n == len(merges) and all(m[2] == 256 + i for i, m in enumerate(merges))
+    assert all(0 <= a < 256 + i and 0 <= b < 256 + i for i, (a, b, _) in enumerate(merges))  # operands exist before use
+    assert len(set((a, b) for a, b, _ in merges)) == n                                          # a pair merges once
+    assert st["n_symbols_live"] == st0["n_symbols_initial"] - st["occurrences"]                 # one symbol dies per occurrence
+    model, vocab = tmp_path / "m", tmp_path / "v"
+    t.save(str(model), str(vocab))
+    # total token frequency mass = number of live symbols weighted by word counts; merges conserve characters
+    lines = vocab.read_bytes().split(b"\n")
+    assert model.stat().st_size == 12 * n
+    o = Oracle(8192, 0, 0.995, 2000); o.load_corpus(p); assert o.train() == n
+    assert o.merges() == merges
+    ov = tmp_path / "ov"; o.save(str(tmp_path / "om"), str(ov))
+    assert ov.read_bytes() == vocab.read_bytes() and len(lines) > 256
+    t.destroy(); o.destroy()
