@@ -262,7 +262,7 @@ def main():
                      "bytes_per_launch": scan_bytes / scan_n if scan_n else None},
         "detail": {"merges_per_step": merges, "n_words": int(st["n_words"]), "n_symbols_initial": int(st["n_symbols_initial"]), "n_symbols_final": int(st["n_symbols_live"]),
                    "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
-                   "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"],
+                   "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
                    "ingest_device_ms": st["ingest_device_ms"], "ingest_gbs": st["ingest_bytes"] / (st["ingest_device_ms"] * 1e-3) / 1e9 if st["ingest_device_ms"] else None,
                    "count_device_ms": st["count_device_ms"], "count_gbs": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 if st["count_device_ms"] else None,
                    "h2d_ms": st["h2d_ms"], "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),

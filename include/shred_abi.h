@@ -110,6 +110,7 @@ typedef struct shred_stats_t {
   uint64_t kernel_launches;      /* every kernel launch since create */
   double load_wall_ms, h2d_ms, train_wall_ms, host_heap_ms, wait_ms, save_wall_ms;
   double train_device_ms;        /* CUDA-event time of the last bpe_train on the engine's stream */
+  double launch_ms;              /* host time spent issuing the per-merge kernel launches */
   uint64_t h2d_bytes, d2h_bytes;
 } shred_stats_t;
 SHRED_API int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);

@@ -17,9 +17,9 @@
 //   k_scatter/k_rank .. hash.cpp:61-72                     word order = (djb2 & 4095, first occurrence)
 //   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids with unk substitution
 //   k_count ........... bpe.cpp:187-218                    adjacent pair counts
-//   k_detect .......... bpe.cpp:265-273                    HBM-bound scan for occurrences of the chosen pair
-//   k_apply ........... bpe.cpp:274-296                    rewrite + emit count deltas
-//   k_finalize ........ bpe.cpp:297-318                    aggregate deltas into the pair table, emit records
+//   k_scan_merge ...... bpe.cpp:265-290,297-318            HBM-bound scan for the chosen pair, per-occurrence count deltas,
+//                                                          last block folds them into the pair table and publishes records
+//   k_rewrite ......... bpe.cpp:291-296                    in-place left-packed rewrite of the touched words
 //   k_token_freq ...... bpe.cpp:409-415                    final token frequencies
 #include <cuda_runtime.h>
 
@@ -72,7 +72,7 @@ __device__ __forceinline__ uint64_t fc_key(int32_t a, int32_t b) {  // bpe.cpp:2
   return (static_cast<uint64_t>(static_cast<int64_t>(a)) << 32) | static_cast<uint64_t>(static_cast<int64_t>(b));
 }
 
-struct Ctrl {  // mapped pinned host memory, written by the last block of k_finalize
+struct Ctrl {  // mapped pinned host memory, written by finalize_block
   volatile uint64_t flag;
   uint64_t n_recs, occ, pt_n, n_leaders, n_keys;
   uint32_t err, pad;
@@ -84,7 +84,7 @@ struct DevCounters {  // device memory
   ull pt_n;
   uint32_t err, pad;
   ull n_tokens;
-  uint32_t n_unique, pad2;
+  uint32_t n_unique, blocks_done2;
 };
 
 struct DeltaTable {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) k_hist_words(const uint8_t* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) k_symbolize(const uint8_t* __restrict__ text, WordTable wt, const uint32_t* order_slot, uint32_t n,
-                                                   const ull* woff, const uint8_t* keep, int32_t unk_code, int32_t* ids) {
+                                                   const ull* woff, const uint8_t* keep, int32_t unk_code, int32_t* ids, uint32_t* wid) {
   __shared__ uint8_t sk[256];
   sk[threadIdx.x] = keep[threadIdx.x];
   __syncthreads();
@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(256) k_symbolize(const uint8_t* __restrict__ t
     const ull first = wt.first[s];
     const ull base = woff[wi];
     ids[base] = static_cast<int32_t>(HDR_BIT | wi);
-    for (uint32_t j = 0; j < len; j++) { const uint32_t c = text[first + j]; ids[base + 1 + j] = sk[c] ? static_cast<int32_t>(c) : unk_code; }
+    wid[base] = wi;
+    for (uint32_t j = 0; j < len; j++) { const uint32_t c = text[first + j]; ids[base + 1 + j] = sk[c] ? static_cast<int32_t>(c) : unk_code; wid[base + 1 + j] = wi; }
   }
 }
 
@@ -381,112 +382,19 @@ __global__ void __launch_bounds__(256) k_count(const int32_t* __restrict__ ids, 
 
 // -------------------------------------------------------------------------------------------------------------- merge
 
-// HBM-bound scan: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs that start in it.  A match
-// whose word has no earlier match is the word's leader and goes to the worklist (position of the word's first symbol).
-template <int UNROLL>
-__global__ void __launch_bounds__(256) k_detect(const int4* __restrict__ ids4, uint32_t n4, int32_t A, int32_t B, uint32_t* __restrict__ wl, DevCounters* ctr) {
-  const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  constexpr uint32_t CHUNK = 32u * UNROLL;
-  for (uint64_t base = static_cast<uint64_t>(warp) * CHUNK; base < n4; base += static_cast<uint64_t>(n_warps) * CHUNK) {
-    int4 v[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const uint64_t i = base + u * 32u + lane;
-      v[u] = i < n4 ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
-    }
-    // first symbol after this chunk (needed by lane 31 of the last row)
-    int32_t after = DEAD;
-    if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldg(ids + 4 * i); }
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
-      const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
-      if (lane == 31) nxt = row_next;
-      uint32_t m = 0;
-      m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
-      m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
-      m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
-      m |= (v[u].w == A && nxt == B) ? 8u : 0u;
-      if (__any_sync(0xFFFFFFFFu, m != 0)) {
-        const uint64_t p0 = (base + u * 32u + lane) * 4u;
-        while (m) {
-          const int k = __ffs(m) - 1;
-          m &= m - 1;
-          // leader test: walk left to the word header; an earlier (A,B) in the same word disqualifies this match
-          uint64_t q = p0 + k;
-          bool leader = true;
-          for (;;) {
-            const int32_t x = ids[q - 1];
-            if (x < 0) break;
-            if (x == A && ids[q] == B) { leader = false; break; }
-            --q;
-          }
-          if (leader) { const uint32_t idx = atomicAdd(&ctr->wl_n, 1u); wl[idx] = static_cast<uint32_t>(q); }
-        }
-      }
-    }
-  }
-}
-
-// One thread per matched word: the reference's left-to-right rewrite (bpe.cpp:268-296), in place, left-packed.
-__global__ void __launch_bounds__(128) k_apply(int32_t* ids, const ull* __restrict__ wcnt, uint32_t* wlen, const uint32_t* __restrict__ wl,
-                                               int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, DevCounters* ctr) {
-  const uint32_t n = ctr->wl_n;
-  uint32_t my_occ = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint64_t q = wl[i];
-    const uint32_t wi = static_cast<uint32_t>(ids[q - 1]) & ~HDR_BIT;
-    const int64_t c = static_cast<int64_t>(wcnt[wi]);
-    uint64_t r = q, w = q;
-    int32_t cur = ids[r];
-    int32_t prev_id = 0; bool have_prev = false;
-    while (cur >= 0) {
-      const int32_t nxt = ids[r + 1];
-      if (cur == A && nxt == B) {
-        ++my_occ;
-        const uint64_t seq = r * 4ull;
-        if (have_prev) {  // left neighbour = current id there (N if just merged), bpe.cpp:274-281
-          dt_add(dt, ctr, fc_key(prev_id, A), -c, seq + 0);
-          dt_add(dt, ctr, fc_key(prev_id, N), c, seq + 1);
-        }
-        const int32_t nn = ids[r + 2];
-        if (nn >= 0) {  // right neighbour = raw next-next id, bpe.cpp:282-290
-          const int32_t rid = code_to_id(nn, P);
-          dt_add(dt, ctr, fc_key(B, rid), -c, seq + 2);
-          dt_add(dt, ctr, fc_key(N, rid), c, seq + 3);
-        }
-        ids[w] = N;
-        prev_id = N; have_prev = true;
-        ++w; r += 2;
-        cur = nn;
-      } else {
-        if (w != r) ids[w] = cur;
-        prev_id = code_to_id(cur, P); have_prev = true;
-        ++w; ++r;
-        cur = nxt;
-      }
-    }
-    for (uint64_t k = w; k < r; k++) ids[k] = DEAD;
-    wlen[wi] = static_cast<uint32_t>(w - q);
-  }
-  for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
-  if ((threadIdx.x & 31) == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
-}
-
-// Aggregated deltas -> pair table (bpe.cpp:297-313, order-free part) + records for the host.  COUNT=true is the
-// bigram-count flavour (bpe.cpp:219-227): no self/phantom handling, PUSH records only.
+// Shared by the count pass (COUNT=true, bpe.cpp:219-227) and the merge pass (bpe.cpp:297-318): fold the aggregated deltas
+// into the pair table and write one record per touched key for the host.  Runs in ONE block (any size): the stand-alone
+// k_finalize_count kernel, or the last block of k_scan_merge to finish.  Ends by publishing the counters to the host and
+// re-arming them.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
-                                                  int32_t A, int32_t B, Params P, uint64_t flag_value) {
+__device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
+                                               int32_t A, int32_t B, const Params& P, uint64_t flag_value) {
   const uint32_t n = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
-  if (!COUNT && blockIdx.x == 0 && threadIdx.x == 0) {  // bpe.cpp:315: the merged pair's frequency becomes 0
+  if (!COUNT && threadIdx.x == 0) {  // bpe.cpp:315: the merged pair's frequency becomes 0
     const uint64_t s = pt_slot(pt, ctr, fc_key(A, B));
     pt.freq[s] = 0ull;
   }
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint32_t ds = dt.list[i];
     const uint64_t key = dt.keys[ds];
     const int64_t d = static_cast<int64_t>(dt.delta[ds]);
@@ -512,24 +420,150 @@ __global__ void __launch_bounds__(128) k_finalize(DeltaTable dt, PairTable pt, D
       if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
     }
   }
-  // last block publishes the counters to the host and re-arms them for the next pass
-  __shared__ bool last;
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
+  if (threadIdx.x == 0) {
     ctrl->n_recs = ctr->rec_n < rec_cap ? ctr->rec_n : rec_cap;
     ctrl->occ = ctr->occ;
     ctrl->pt_n = ctr->pt_n;
     ctrl->n_leaders = ctr->wl_n;
     ctrl->n_keys = ctr->dt_n;
     ctrl->err = ctr->err;
-    ctr->wl_n = 0; ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->occ = 0ull;
+    ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->occ = 0ull;
     __threadfence_system();
     ctrl->flag = flag_value;
   }
+}
+
+__global__ void __launch_bounds__(256) k_finalize_count(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
+                                                        uint64_t flag_value) {
+  finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
+}
+
+// One occurrence of (A,B) at flat position p: the four count deltas of bpe.cpp:274-290, computed independently per
+// occurrence.  Left neighbour = the id that stands there when the reference's left-to-right pass reaches p (N if the two
+// symbols before p were themselves merged in this pass), right neighbour = the raw id two slots on.
+__device__ __forceinline__ void emit_occurrence(const int32_t* __restrict__ ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
+                                                int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
+                                                uint32_t& my_occ) {
+  const int32_t l1 = ids[p - 1];
+  bool left_merged;
+  if (A != B) {
+    left_merged = l1 == B && ids[p - 2] == A;  // (A,B) pairs cannot overlap when A != B
+  } else {
+    uint64_t q = p;  // start of the run of A's: pairs are taken greedily from there (bpe.cpp:268-295)
+    while (ids[q - 1] == A) --q;
+    if ((p - q) & 1ull) return;  // second half of a merged pair, not an occurrence
+    left_merged = p > q;
+  }
+  const int64_t c = static_cast<int64_t>(wcnt[wid[p]]);
+  const uint64_t seq = p * 4ull;
+  if (l1 >= 0) {
+    const int32_t lid = left_merged ? N : code_to_id(l1, P);
+    dt_add(dt, ctr, fc_key(lid, A), -c, seq + 0);
+    dt_add(dt, ctr, fc_key(lid, N), c, seq + 1);
+  }
+  const int32_t r2 = ids[p + 2];
+  if (r2 >= 0) {
+    const int32_t rid = code_to_id(r2, P);
+    dt_add(dt, ctr, fc_key(B, rid), -c, seq + 2);
+    dt_add(dt, ctr, fc_key(N, rid), c, seq + 3);
+  }
+  ml[atomicAdd(&ctr->wl_n, 1u)] = static_cast<uint32_t>(p);
+  ++my_occ;
+}
+
+// The per-merge pass.  HBM-bound scan: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs that start
+// in it; an occurrence emits its count deltas straight into the delta table and is remembered for the rewrite kernel.
+// The last block to finish folds the deltas into the pair table and publishes the records to the host (finalize_block),
+// so the host can replay its heap while k_rewrite is still running.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_scan_merge(const int4* __restrict__ ids4, uint32_t n4, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
+                                                    int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt, DevCounters* ctr,
+                                                    uint32_t* __restrict__ ml, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, uint64_t flag_value) {
+  const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  constexpr uint32_t CHUNK = 32u * UNROLL;
+  uint32_t my_occ = 0;
+  for (uint64_t base = static_cast<uint64_t>(warp) * CHUNK; base < n4; base += static_cast<uint64_t>(n_warps) * CHUNK) {
+    int4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const uint64_t i = base + u * 32u + lane;
+      v[u] = i < n4 ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+    }
+    int32_t after = DEAD;  // first symbol after this chunk (needed by lane 31 of the last row)
+    if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldg(ids + 4 * i); }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
+      const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
+      if (lane == 31) nxt = row_next;
+      uint32_t m = 0;
+      m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
+      m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
+      m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
+      m |= (v[u].w == A && nxt == B) ? 8u : 0u;
+      if (__any_sync(0xFFFFFFFFu, m != 0)) {
+        const uint64_t p0 = (base + u * 32u + lane) * 4u;
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ);
+        }
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
+  if (lane == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
+  // last block out folds the deltas and publishes
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    finalize_block<false>(dt, pt, ctr, recs, rec_cap, ctrl, A, B, P, flag_value);
+  }
+}
+
+// Rewrites every word that holds an occurrence: the reference's left-to-right relink (bpe.cpp:268-296) as an in-place,
+// left-packed rewrite of the word's slot.  The first occurrence to claim the word (claimed[wi] = merge number) does it.
+__global__ void __launch_bounds__(128) k_rewrite(int32_t* ids, const uint32_t* __restrict__ wid, const ull* __restrict__ woff, uint32_t* wlen,
+                                                 uint32_t* claimed, const uint32_t* __restrict__ ml, int32_t A, int32_t B, int32_t N, uint32_t merge_no,
+                                                 DevCounters* ctr) {
+  const uint32_t n = ctr->wl_n;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t wi = wid[ml[i]];
+    if (atomicMax(&claimed[wi], merge_no) >= merge_no) continue;
+    const uint64_t q = woff[wi] + 1;
+    uint64_t r = q, w = q;
+    int32_t cur = ids[r];
+    while (cur >= 0) {
+      const int32_t nxt = ids[r + 1];
+      if (cur == A && nxt == B) {
+        const int32_t nn = ids[r + 2];
+        ids[w] = N;
+        ++w; r += 2;
+        cur = nn;
+      } else {
+        if (w != r) ids[w] = cur;
+        ++w; ++r;
+        cur = nxt;
+      }
+    }
+    for (uint64_t k = w; k < r; k++) ids[k] = DEAD;
+    wlen[wi] = static_cast<uint32_t>(w - q);
+  }
+  // last block re-arms the match counter for the next merge
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done2, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) { ctr->wl_n = 0; ctr->blocks_done2 = 0; }
 }
 
 __global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {
@@ -551,11 +585,11 @@ __global__ void k_len1(const uint32_t* wlen, uint32_t n, ull* len1) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) len1[i] = static_cast<ull>(wlen[i]) + 1ull;
 }
 __global__ void k_compact(const int32_t* __restrict__ src, const ull* __restrict__ old_off, const ull* __restrict__ new_off, const uint32_t* __restrict__ wlen,
-                          uint32_t n, int32_t* dst) {
+                          uint32_t n, int32_t* dst, uint32_t* dst_wid) {
   for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
     const ull so = old_off[wi], d = new_off[wi];
     const uint32_t len = wlen[wi];
-    for (uint32_t j = 0; j <= len; j++) dst[d + j] = src[so + j];
+    for (uint32_t j = 0; j <= len; j++) { dst[d + j] = src[so + j]; dst_wid[d + j] = wi; }
   }
 }
 __global__ void k_token_freq(const int32_t* __restrict__ ids, const ull* __restrict__ woff, const uint32_t* __restrict__ wlen, const ull* __restrict__ wcnt,
@@ -595,6 +629,8 @@ class CudaEngine : public Engine {
     CK(cudaEventCreate(&ev1_));
     CK(cudaEventCreate(&evm0_));
     CK(cudaEventCreate(&evm1_));
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_merge<4>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     return 0;
@@ -716,10 +752,15 @@ class CudaEngine : public Engine {
     ids_cap_ = ((S1 + 8 + 1023) / 1024) * 1024;
     CK(cudaMalloc(reinterpret_cast<void**>(&ids_[0]), ids_cap_ * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&ids_[1]), ids_cap_ * 4));
     CK(cudaMalloc(reinterpret_cast<void**>(&wl_), ids_cap_ * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&wid_[0]), ids_cap_ * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&wid_[1]), ids_cap_ * 4));
+    CK(cudaMalloc(reinterpret_cast<void**>(&claimed_), Na * 4));
+    CK(cudaMemsetAsync(claimed_, 0, Na * 4, st_));
+    CK(cudaMemsetAsync(wid_[0], 0, ids_cap_ * 4, st_)); CK(cudaMemsetAsync(wid_[1], 0, ids_cap_ * 4, st_));
+    merge_no_ = 0;
     cur_ = 0;
     CK(cudaMemcpyAsync(d_keep, info->keep, 256, cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(woff_[0] + N, &S1, 8, cudaMemcpyHostToDevice, st_));
-    if (N) { k_symbolize<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, woff_[0], d_keep, P_.unk_code, ids_[0]); launches_++; es_.ingest_launches++; }
+    if (N) { k_symbolize<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, woff_[0], d_keep, P_.unk_code, ids_[0], wid_[0]); launches_++; es_.ingest_launches++; }
     k_fill_i32<<<grid_for(ids_cap_ - S1, 256), 256, 0, st_>>>(ids_[0], S1, ids_cap_, DEAD); launches_++; es_.ingest_launches++;
     CK(cudaStreamSynchronize(st_));
     CK(cudaGetLastError());
@@ -798,7 +839,7 @@ class CudaEngine : public Engine {
         continue;
       }
       RC(grow_pt(static_cast<uint64_t>(c.dt_n) + 4ull * (256 + vocab_hint_) + 1024));
-      k_finalize<true><<<fin_grid(), 128, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), 0, 0, P_, flag_); launches_++;
+      k_finalize_count<<<1, 256, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), P_, flag_); launches_++;
       RC(wait_flag());
       if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", ctrl_->err); return -1; }
       es_.count_launches++; es_.count_device_ms += ms; es_.count_bytes += 4.0 * static_cast<double>(n_live_) + 12.0 * n_words_;
@@ -820,14 +861,17 @@ class CudaEngine : public Engine {
     // reclaim dead slots once a quarter of the scanned array is dead
     if (n_slots_ > 4096 && (n_slots_ - n_live_) * 4 > n_slots_) RC(compact());
     const uint32_t n4 = static_cast<uint32_t>((n_slots_ + 3) / 4);
+    const double tl0 = now_ms();
     ++flag_;
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
     if (timed) CK(cudaEventRecord(ev0_, st_));
-    k_detect<4><<<detect_grid(n4), 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_[cur_]), n4, a, b, wl_, ctr_);
+    ++merge_no_;
+    k_scan_merge<4><<<detect_grid(n4), 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_[cur_]), n4, wid_[cur_], wcnt_, a, b, new_id, P_, dt_, pt_, ctr_, wl_,
+                                                       recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), flag_);
     if (timed) CK(cudaEventRecord(ev1_, st_));
-    k_apply<<<n_sm_ * 2, 128, 0, st_>>>(ids_[cur_], wcnt_, wlen_, wl_, a, b, new_id, P_, dt_, ctr_);
-    k_finalize<false><<<fin_grid(), 128, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), a, b, P_, flag_);
-    launches_ += 3;
+    k_rewrite<<<n_sm_, 128, 0, st_>>>(ids_[cur_], wid_[cur_], woff_[cur_], wlen_, claimed_, wl_, a, b, new_id, merge_no_, ctr_);
+    launches_ += 2;
+    launch_ms_ += now_ms() - tl0;
     RC(wait_flag());
     if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
     if (timed) {
@@ -858,7 +902,7 @@ class CudaEngine : public Engine {
     CK(cudaMemcpyAsync(&S1, sums + nb_scan, 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
     CK(cudaMemcpyAsync(woff_[nxt] + N, &S1, 8, cudaMemcpyHostToDevice, st_));
-    k_compact<<<grid_for(N, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], woff_[nxt], wlen_, N, ids_[nxt]);
+    k_compact<<<grid_for(N, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], woff_[nxt], wlen_, N, ids_[nxt], wid_[nxt]);
     const uint64_t pad_to = ((S1 + 8 + 1023) / 1024) * 1024;
     k_fill_i32<<<grid_for(pad_to - S1, 256), 256, 0, st_>>>(ids_[nxt], S1, pad_to < ids_cap_ ? pad_to : ids_cap_, DEAD);
     launches_ += 6;
@@ -937,7 +981,7 @@ class CudaEngine : public Engine {
   void stats(EngineStats* out) override {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
-    out->kernel_launches = launches_; out->wait_ms = wait_ms_;
+    out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_;
   }
   const char* name() override { return name_; }
 
@@ -947,13 +991,12 @@ class CudaEngine : public Engine {
     if (g < 1) g = 1;
     return static_cast<int>(g < maxg ? g : maxg);
   }
-  int detect_grid(uint32_t n4) const {  // a multiple of the SM count, 8 CTAs of 256 threads per SM at most
+  int detect_grid(uint32_t n4) const {  // persistent grid: SM count x resident CTAs per SM (occupancy query), never more than the work
     uint64_t warps_needed = (static_cast<uint64_t>(n4) + 127) / 128, ctas = (warps_needed + 7) / 8;
-    uint64_t maxg = static_cast<uint64_t>(n_sm_) * 8;
+    uint64_t maxg = static_cast<uint64_t>(n_sm_) * scan_ctas_per_sm_;
     if (ctas < 1) ctas = 1;
     return static_cast<int>(ctas < maxg ? ctas : maxg);
   }
-  int fin_grid() const { return n_sm_ < 32 ? n_sm_ : 32; }
 
   int wait_flag() {
     double t0 = now_ms();
@@ -978,6 +1021,8 @@ class CudaEngine : public Engine {
     if (wcnt_) cudaFree(wcnt_); wcnt_ = nullptr;
     if (wlen_) cudaFree(wlen_); wlen_ = nullptr;
     if (wl_) cudaFree(wl_); wl_ = nullptr;
+    for (int i = 0; i < 2; i++) { if (wid_[i]) cudaFree(wid_[i]); wid_[i] = nullptr; }
+    if (claimed_) cudaFree(claimed_); claimed_ = nullptr;
     n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
   }
   void release_all() {
@@ -1010,6 +1055,9 @@ class CudaEngine : public Engine {
   ull* wcnt_ = nullptr;
   uint32_t* wlen_ = nullptr;
   uint32_t* wl_ = nullptr;
+  uint32_t* wid_[2] = {nullptr, nullptr};
+  uint32_t* claimed_ = nullptr;
+  uint32_t merge_no_ = 0;
   DeltaTable dt_{};
   PairTable pt_{};
   uint64_t pt_n_ = 0;
@@ -1021,8 +1069,9 @@ class CudaEngine : public Engine {
   uint64_t vocab_hint_ = 32768;
   EngineStats es_{};
   uint64_t launches_ = 0, merge_seq_ = 0;
-  double wait_ms_ = 0;
+  double wait_ms_ = 0, launch_ms_ = 0;
   int timing_every_ = 0;
+  int scan_ctas_per_sm_ = 4;
 };
 
 char g_devname[320] = "no CUDA device";

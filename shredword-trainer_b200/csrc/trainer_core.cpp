@@ -330,7 +330,7 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->ingest_launches = es.ingest_launches; s->ingest_device_ms = es.ingest_device_ms; s->ingest_bytes = es.ingest_bytes;
   s->kernel_launches = es.kernel_launches;
   s->load_wall_ms = load_wall_ms_; s->h2d_ms = es.h2d_ms; s->train_wall_ms = train_wall_ms_; s->train_device_ms = train_device_ms_; s->host_heap_ms = host_heap_ms_;
-  s->wait_ms = es.wait_ms; s->save_wall_ms = save_wall_ms_;
+  s->wait_ms = es.wait_ms; s->launch_ms = es.launch_ms; s->save_wall_ms = save_wall_ms_;
   s->h2d_bytes = es.h2d_bytes; s->d2h_bytes = es.d2h_bytes;
 }
 
