@@ -173,7 +173,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["SHRED_QUIET"] = "1"
-    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "4")  # CUDA events around every 4th merge scan
+    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "16")  # CUDA events around every 16th merge scan
     os.environ["SHRED_DEVICE"] = str(local_rank)
     import __graft_entry__ as ge
     if rank == 0:

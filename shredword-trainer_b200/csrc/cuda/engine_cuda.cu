@@ -390,7 +390,7 @@ template <bool COUNT>
 __device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
                                                int32_t A, int32_t B, const Params& P, uint64_t flag_value) {
   const uint32_t n = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
-  if (!COUNT && threadIdx.x == 0) {  // bpe.cpp:315: the merged pair's frequency becomes 0
+  if (!COUNT && threadIdx.x == blockDim.x - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
     const uint64_t s = pt_slot(pt, ctr, fc_key(A, B));
     pt.freq[s] = 0ull;
   }
@@ -447,6 +447,8 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* __restrict__ ids,
                                                 int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
                                                 uint32_t& my_occ) {
   const int32_t l1 = ids[p - 1];
+  const uint32_t wi = wid[p];  // independent loads first: wid -> wcnt is the longest chain
+  const int32_t r2 = ids[p + 2];
   bool left_merged;
   if (A != B) {
     left_merged = l1 == B && ids[p - 2] == A;  // (A,B) pairs cannot overlap when A != B
@@ -456,14 +458,13 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* __restrict__ ids,
     if ((p - q) & 1ull) return;  // second half of a merged pair, not an occurrence
     left_merged = p > q;
   }
-  const int64_t c = static_cast<int64_t>(wcnt[wid[p]]);
+  const int64_t c = static_cast<int64_t>(wcnt[wi]);
   const uint64_t seq = p * 4ull;
   if (l1 >= 0) {
     const int32_t lid = left_merged ? N : code_to_id(l1, P);
     dt_add(dt, ctr, fc_key(lid, A), -c, seq + 0);
     dt_add(dt, ctr, fc_key(lid, N), c, seq + 1);
   }
-  const int32_t r2 = ids[p + 2];
   if (r2 >= 0) {
     const int32_t rid = code_to_id(r2, P);
     dt_add(dt, ctr, fc_key(B, rid), -c, seq + 2);
@@ -540,6 +541,8 @@ __global__ void __launch_bounds__(128) k_rewrite(int32_t* ids, const uint32_t* _
     const uint32_t wi = wid[ml[i]];
     if (atomicMax(&claimed[wi], merge_no) >= merge_no) continue;
     const uint64_t q = woff[wi] + 1;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ids + q));        // the walk below is a chain of dependent loads:
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ids + q + 32));   // pull the word's lines into L1 first
     uint64_t r = q, w = q;
     int32_t cur = ids[r];
     while (cur >= 0) {
@@ -623,12 +626,14 @@ class CudaEngine : public Engine {
     CK(cudaHostAlloc(&cp, sizeof(Ctrl), cudaHostAllocMapped));
     std::memset(cp, 0, sizeof(Ctrl));
     ctrl_ = static_cast<volatile Ctrl*>(cp);
-    CK(cudaMalloc(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters)));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters), st_));
     CK(cudaMemset(ctr_, 0, sizeof(DevCounters)));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
     CK(cudaEventCreate(&evm0_));
     CK(cudaEventCreate(&evm1_));
+    cudaMemPool_t pool;  // stream-ordered allocations; keep freed blocks cached so repeated loads do not pay cudaMalloc
+    if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_merge<4>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
     const char* e = std::getenv("SHRED_TIMING");
@@ -650,7 +655,7 @@ class CudaEngine : public Engine {
     // --- corpus bytes to HBM, padded with spaces so token walks and 16-byte loads stay in bounds
     const uint64_t padded = ((n + 15) & ~15ull) + 64;
     uint8_t* d_text = nullptr;
-    CK(cudaMalloc(reinterpret_cast<void**>(&d_text), padded));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_text), padded, st_));
     double t0 = now_ms();
     if (n) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
     CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
@@ -659,7 +664,7 @@ class CudaEngine : public Engine {
 
     CK(cudaEventRecord(ev0_, st_));
     int rc = ingest(d_text, n, info);
-    cudaFree(d_text);
+    cudaFreeAsync(d_text, st_);
     if (rc != 0) return rc;
     CK(cudaEventRecord(ev1_, st_));
     CK(cudaStreamSynchronize(st_));
@@ -678,9 +683,9 @@ class CudaEngine : public Engine {
     for (int attempt = 0;; ++attempt) {
       if (attempt > 8) { std::fprintf(stderr, "[ERROR]\t unique-word table did not converge\n"); return -1; }
       if (cap > (1ull << 32)) { std::fprintf(stderr, "[ERROR]\t unique-word table too large\n"); return -1; }
-      CK(cudaMalloc(reinterpret_cast<void**>(&wt.tag), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&wt.first), cap * 8));
-      CK(cudaMalloc(reinterpret_cast<void**>(&wt.count), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&wt.len), cap * 4));
-      CK(cudaMalloc(reinterpret_cast<void**>(&wt.bucket), cap * 4));
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.tag), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.first), cap * 8, st_));
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.count), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.len), cap * 4, st_));
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.bucket), cap * 4, st_));
       wt.cap = cap; wt.mask = cap - 1;
       CK(cudaMemsetAsync(wt.tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt.first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt.count, 0, cap * 8, st_));
       CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
@@ -690,12 +695,12 @@ class CudaEngine : public Engine {
       CK(cudaStreamSynchronize(st_));
       CK(cudaGetLastError());
       if (c.err & ERR_HAS_NUL) {
-        cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket);
+        cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_);
         return 1;
       }
       const bool too_full = static_cast<uint64_t>(c.n_unique) * 2 > cap;
       if ((c.err & (ERR_WT_FULL | ERR_WT_COLLISION)) || too_full) {
-        cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket);
+        cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_);
         if ((c.err & ERR_WT_FULL) || too_full) cap *= 4;
         if (c.err & ERR_WT_COLLISION) seed = seed * 2654435761u + 12345u;
         continue;
@@ -703,7 +708,7 @@ class CudaEngine : public Engine {
       N = c.n_unique; n_tokens = c.n_tokens;
       break;
     }
-    auto free_wt = [&]() { cudaFree(wt.tag); cudaFree(wt.first); cudaFree(wt.count); cudaFree(wt.len); cudaFree(wt.bucket); };
+    auto free_wt = [&]() { cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_); };
     if (N >= 0x7FFFFFF0u) { free_wt(); std::fprintf(stderr, "[ERROR]\t too many unique words\n"); return -1; }
     n_words_ = N;
     info->n_words = N; info->n_tokens = n_tokens;
@@ -712,22 +717,22 @@ class CudaEngine : public Engine {
     ull *tmp_first = nullptr, *d_hist = nullptr, *len1 = nullptr, *sums = nullptr;
     uint8_t* d_keep = nullptr;
     const uint64_t Na = N ? N : 1;
-    CK(cudaMalloc(reinterpret_cast<void**>(&u_slot), Na * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&tmp_slot), Na * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&order_slot), Na * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&tmp_first), Na * 8));
-    CK(cudaMalloc(reinterpret_cast<void**>(&len1), Na * 8));
-    CK(cudaMalloc(reinterpret_cast<void**>(&u_n), 4)); CK(cudaMalloc(reinterpret_cast<void**>(&bcnt), 4096 * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&bstart), 4097 * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&cursor), 4096 * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&d_hist), 256 * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&d_keep), 256));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&u_slot), Na * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&tmp_slot), Na * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&order_slot), Na * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&tmp_first), Na * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&len1), Na * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&u_n), 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&bcnt), 4096 * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&bstart), 4097 * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&cursor), 4096 * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_hist), 256 * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&d_keep), 256, st_));
     const uint32_t nb_scan = static_cast<uint32_t>((Na + SCAN_TILE - 1) / SCAN_TILE);
-    CK(cudaMalloc(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8, st_));
     auto free_tmp = [&]() {
-      cudaFree(u_slot); cudaFree(tmp_slot); cudaFree(order_slot); cudaFree(tmp_first); cudaFree(len1); cudaFree(u_n); cudaFree(bcnt);
-      cudaFree(bstart); cudaFree(cursor); cudaFree(d_hist); cudaFree(d_keep); cudaFree(sums);
+      cudaFreeAsync(u_slot, st_); cudaFreeAsync(tmp_slot, st_); cudaFreeAsync(order_slot, st_); cudaFreeAsync(tmp_first, st_); cudaFreeAsync(len1, st_); cudaFreeAsync(u_n, st_); cudaFreeAsync(bcnt, st_);
+      cudaFreeAsync(bstart, st_); cudaFreeAsync(cursor, st_); cudaFreeAsync(d_hist, st_); cudaFreeAsync(d_keep, st_); cudaFreeAsync(sums, st_);
     };
     CK(cudaMemsetAsync(u_n, 0, 4, st_)); CK(cudaMemsetAsync(bcnt, 0, 4096 * 4, st_)); CK(cudaMemsetAsync(cursor, 0, 4096 * 4, st_));
     CK(cudaMemsetAsync(d_hist, 0, 256 * 8, st_));
-    CK(cudaMalloc(reinterpret_cast<void**>(&wcnt_), Na * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&wlen_), Na * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&woff_[0]), (Na + 1) * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&woff_[1]), (Na + 1) * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wcnt_), Na * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wlen_), Na * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&woff_[0]), (Na + 1) * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&woff_[1]), (Na + 1) * 8, st_));
     ull S1 = 0;  // total slots = symbols + headers
     if (N) {
       k_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, bcnt);
@@ -750,10 +755,10 @@ class CudaEngine : public Engine {
     n_slots_ = S1; n_live_ = S1;
     if (S1 + 64 >= (1ull << 32)) { free_tmp(); free_wt(); std::fprintf(stderr, "[ERROR]\t corpus needs more than 2^32 symbol slots on one GPU\n"); return -1; }
     ids_cap_ = ((S1 + 8 + 1023) / 1024) * 1024;
-    CK(cudaMalloc(reinterpret_cast<void**>(&ids_[0]), ids_cap_ * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&ids_[1]), ids_cap_ * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&wl_), ids_cap_ * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&wid_[0]), ids_cap_ * 4)); CK(cudaMalloc(reinterpret_cast<void**>(&wid_[1]), ids_cap_ * 4));
-    CK(cudaMalloc(reinterpret_cast<void**>(&claimed_), Na * 4));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&ids_[0]), ids_cap_ * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&ids_[1]), ids_cap_ * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wl_), ids_cap_ * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wid_[0]), ids_cap_ * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wid_[1]), ids_cap_ * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&claimed_), Na * 4, st_));
     CK(cudaMemsetAsync(claimed_, 0, Na * 4, st_));
     CK(cudaMemsetAsync(wid_[0], 0, ids_cap_ * 4, st_)); CK(cudaMemsetAsync(wid_[1], 0, ids_cap_ * 4, st_));
     merge_no_ = 0;
@@ -784,9 +789,9 @@ class CudaEngine : public Engine {
     return 0;
   }
   int alloc_dt(uint64_t cap) {
-    if (dt_.keys) { cudaFree(dt_.keys); cudaFree(dt_.delta); cudaFree(dt_.seq); cudaFree(dt_.list); dt_.keys = nullptr; }
-    CK(cudaMalloc(reinterpret_cast<void**>(&dt_.keys), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&dt_.delta), cap * 8));
-    CK(cudaMalloc(reinterpret_cast<void**>(&dt_.seq), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&dt_.list), cap * 4));
+    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); dt_.keys = nullptr; }
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.keys), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.delta), cap * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.seq), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.list), cap * 4, st_));
     dt_.cap = static_cast<uint32_t>(cap); dt_.mask = cap - 1;
     // a key value no pair can produce: high word >= 2^31 that is neither all-ones nor unk_id
     uint32_t hi = 0x80000000u; if (static_cast<uint32_t>(cfg_.unk_id) == hi) hi = 0x80000001u;
@@ -798,7 +803,7 @@ class CudaEngine : public Engine {
     return 0;
   }
   int alloc_pt(PairTable* pt, uint64_t cap) {
-    CK(cudaMalloc(reinterpret_cast<void**>(&pt->keys), cap * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&pt->freq), cap * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->keys), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->freq), cap * 8, st_));
     pt->cap = cap; pt->mask = cap - 1;
     CK(cudaMemsetAsync(pt->keys, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(pt->freq, 0, cap * 8, st_));
     return 0;
@@ -810,7 +815,7 @@ class CudaEngine : public Engine {
     RC(alloc_pt(&nt, cap));
     k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
     CK(cudaStreamSynchronize(st_));
-    cudaFree(pt_.keys); cudaFree(pt_.freq);
+    cudaFreeAsync(pt_.keys, st_); cudaFreeAsync(pt_.freq, st_);
     pt_ = nt;
     return 0;
   }
@@ -854,6 +859,7 @@ class CudaEngine : public Engine {
   // --------------------------------------------------------------------------------------------------------- merge
   int merge(int32_t a, int32_t b, int32_t new_id, const Rec** recs, size_t* n, uint64_t* occurrences) override {
     *recs = recs_; *n = 0; *occurrences = 0;
+    const double tm0 = now_ms();
     // keep the pair table at most half full even if this merge creates every key it can (4 per distinct id)
     const uint64_t worst_new = 4ull * (static_cast<uint64_t>(new_id) + 2);
     if ((pt_n_ + worst_new) * 2 > pt_.cap) RC(grow_pt(pt_n_ + worst_new));
@@ -884,6 +890,7 @@ class CudaEngine : public Engine {
     pt_n_ = ctrl_->pt_n;
     n_live_ -= ctrl_->occ;
     es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
+    merge_ms_ += now_ms() - tm0;
     return 0;
   }
 
@@ -892,7 +899,7 @@ class CudaEngine : public Engine {
     if (!N) return 0;
     ull *len1 = nullptr, *sums = nullptr;
     const uint32_t nb_scan = (N + SCAN_TILE - 1) / SCAN_TILE;
-    CK(cudaMalloc(reinterpret_cast<void**>(&len1), static_cast<uint64_t>(N) * 8)); CK(cudaMalloc(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&len1), static_cast<uint64_t>(N) * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8, st_));
     const int nxt = cur_ ^ 1;
     k_len1<<<grid_for(N, 256), 256, 0, st_>>>(wlen_, N, len1);
     k_scan_sums<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums);
@@ -908,7 +915,7 @@ class CudaEngine : public Engine {
     launches_ += 6;
     CK(cudaStreamSynchronize(st_));
     CK(cudaGetLastError());
-    cudaFree(len1); cudaFree(sums);
+    cudaFreeAsync(len1, st_); cudaFreeAsync(sums, st_);
     cur_ = nxt; n_slots_ = S1; n_live_ = S1;
     es_.compactions++;
     return 0;
@@ -919,12 +926,12 @@ class CudaEngine : public Engine {
     CK(cudaSetDevice(dev_));
     if (!loaded_ || !n_words_ || !T) return 0;
     ull* d = nullptr;
-    CK(cudaMalloc(reinterpret_cast<void**>(&d), T * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d), T * 8, st_));
     CK(cudaMemsetAsync(d, 0, T * 8, st_));
     k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, d, T); launches_++;
     CK(cudaMemcpyAsync(freq, d, T * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
-    cudaFree(d);
+    cudaFreeAsync(d, st_);
     es_.d2h_bytes += T * 8;
     return 0;
   }
@@ -981,7 +988,7 @@ class CudaEngine : public Engine {
   void stats(EngineStats* out) override {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
-    out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_;
+    out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_; out->merge_ms = merge_ms_;
   }
   const char* name() override { return name_; }
 
@@ -1017,22 +1024,23 @@ class CudaEngine : public Engine {
   }
 
   void release_corpus() {
-    for (int i = 0; i < 2; i++) { if (ids_[i]) cudaFree(ids_[i]); ids_[i] = nullptr; if (woff_[i]) cudaFree(woff_[i]); woff_[i] = nullptr; }
-    if (wcnt_) cudaFree(wcnt_); wcnt_ = nullptr;
-    if (wlen_) cudaFree(wlen_); wlen_ = nullptr;
-    if (wl_) cudaFree(wl_); wl_ = nullptr;
-    for (int i = 0; i < 2; i++) { if (wid_[i]) cudaFree(wid_[i]); wid_[i] = nullptr; }
-    if (claimed_) cudaFree(claimed_); claimed_ = nullptr;
+    for (int i = 0; i < 2; i++) { if (ids_[i]) cudaFreeAsync(ids_[i], st_); ids_[i] = nullptr; if (woff_[i]) cudaFreeAsync(woff_[i], st_); woff_[i] = nullptr; }
+    if (wcnt_) cudaFreeAsync(wcnt_, st_); wcnt_ = nullptr;
+    if (wlen_) cudaFreeAsync(wlen_, st_); wlen_ = nullptr;
+    if (wl_) cudaFreeAsync(wl_, st_); wl_ = nullptr;
+    for (int i = 0; i < 2; i++) { if (wid_[i]) cudaFreeAsync(wid_[i], st_); wid_[i] = nullptr; }
+    if (claimed_) cudaFreeAsync(claimed_, st_); claimed_ = nullptr;
     n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
   }
   void release_all() {
     cudaSetDevice(dev_);
     release_corpus();
-    if (dt_.keys) { cudaFree(dt_.keys); cudaFree(dt_.delta); cudaFree(dt_.seq); cudaFree(dt_.list); }
-    if (pt_.keys) { cudaFree(pt_.keys); cudaFree(pt_.freq); }
+    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); }
+    if (pt_.keys) { cudaFreeAsync(pt_.keys, st_); cudaFreeAsync(pt_.freq, st_); }
     if (recs_) cudaFreeHost(recs_);
     if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
-    if (ctr_) cudaFree(ctr_);
+    if (ctr_) cudaFreeAsync(ctr_, st_);
+    if (st_) cudaStreamSynchronize(st_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (evm0_) cudaEventDestroy(evm0_);
@@ -1069,7 +1077,7 @@ class CudaEngine : public Engine {
   uint64_t vocab_hint_ = 32768;
   EngineStats es_{};
   uint64_t launches_ = 0, merge_seq_ = 0;
-  double wait_ms_ = 0, launch_ms_ = 0;
+  double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0;
   int timing_every_ = 0;
   int scan_ctas_per_sm_ = 4;
 };

@@ -45,7 +45,7 @@ struct EngineStats {
   uint64_t count_launches; double count_device_ms; double count_bytes;
   uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;
   uint64_t kernel_launches;
-  double h2d_ms, wait_ms, launch_ms;
+  double h2d_ms, wait_ms, launch_ms, merge_ms;
   uint64_t h2d_bytes, d2h_bytes;
 };
 

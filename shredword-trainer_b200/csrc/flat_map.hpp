@@ -1,4 +1,6 @@
 // flat_map.hpp -- minimal open-addressing u64 -> V map for the host control path (pair versions, phantom pairs).
+// One 16-byte cell per entry (key, value, used) so a lookup touches one cache line; prefetch() lets the caller overlap
+// the miss with other work (the heap replay does ~110 lookups per merge into a table of millions of pairs).
 #pragma once
 #include <cstdint>
 #include <cstdlib>
@@ -13,40 +15,43 @@ inline uint64_t mix64(uint64_t x) {
 
 template <class V>
 class FlatMap {
+  struct Cell { uint64_t key; V val; uint32_t used; };
+
  public:
-  void clear() { keys_.clear(); vals_.clear(); used_.clear(); n_ = 0; }
+  void clear() { cells_.clear(); n_ = 0; }
   size_t size() const { return n_; }
+  void prefetch(uint64_t k) const {
+    if (!cells_.empty()) __builtin_prefetch(&cells_[mix64(k) & (cells_.size() - 1)]);
+  }
   // get-or-create, value-initialised
   V& operator[](uint64_t k) {
-    if ((n_ + 1) * 2 > keys_.size()) grow();
-    size_t m = keys_.size() - 1, s = mix64(k) & m;
-    while (used_[s]) { if (keys_[s] == k) return vals_[s]; s = (s + 1) & m; }
-    used_[s] = 1; keys_[s] = k; vals_[s] = V(); ++n_;
-    return vals_[s];
+    if ((n_ + 1) * 2 > cells_.size()) grow();
+    size_t m = cells_.size() - 1, s = mix64(k) & m;
+    while (cells_[s].used) { if (cells_[s].key == k) return cells_[s].val; s = (s + 1) & m; }
+    cells_[s].used = 1; cells_[s].key = k; cells_[s].val = V(); ++n_;
+    return cells_[s].val;
   }
   V* find(uint64_t k) {
-    if (keys_.empty()) return nullptr;
-    size_t m = keys_.size() - 1, s = mix64(k) & m;
-    while (used_[s]) { if (keys_[s] == k) return &vals_[s]; s = (s + 1) & m; }
+    if (cells_.empty()) return nullptr;
+    size_t m = cells_.size() - 1, s = mix64(k) & m;
+    while (cells_[s].used) { if (cells_[s].key == k) return &cells_[s].val; s = (s + 1) & m; }
     return nullptr;
   }
 
  private:
   void grow() {
-    size_t nc = keys_.empty() ? 1024 : keys_.size() * 2;
-    std::vector<uint64_t> ok; std::vector<V> ov; std::vector<uint8_t> ou;
-    ok.swap(keys_); ov.swap(vals_); ou.swap(used_);
-    keys_.assign(nc, 0); vals_.assign(nc, V()); used_.assign(nc, 0);
+    size_t nc = cells_.empty() ? 1024 : cells_.size() * 2;
+    std::vector<Cell> old;
+    old.swap(cells_);
+    cells_.assign(nc, Cell{0, V(), 0});
     size_t m = nc - 1;
-    for (size_t i = 0; i < ok.size(); i++) if (ou[i]) {
-      size_t s = mix64(ok[i]) & m;
-      while (used_[s]) s = (s + 1) & m;
-      used_[s] = 1; keys_[s] = ok[i]; vals_[s] = ov[i];
+    for (const Cell& c : old) if (c.used) {
+      size_t s = mix64(c.key) & m;
+      while (cells_[s].used) s = (s + 1) & m;
+      cells_[s] = c;
     }
   }
-  std::vector<uint64_t> keys_;
-  std::vector<V> vals_;
-  std::vector<uint8_t> used_;
+  std::vector<Cell> cells_;
   size_t n_ = 0;
 };
 

@@ -187,6 +187,7 @@ void TrainerCore::apply_records(const Rec* recs, size_t n) {
     return x.seq > y.seq;
   });
   const uint64_t min_freq = abi_->config.min_pair_freq;
+  for (const Rec& r : order_) version_.prefetch(r.key);
   for (const Rec& r : order_) {
     PairKey pk = unpack_key(r.key);
     switch (r.kind) {
@@ -218,6 +219,7 @@ int TrainerCore::merge_batch(int batch_size) {
   int done = 0;
   while (done < batch_size && !heap_.empty()) {
     double h0 = now_ms();
+    version_.prefetch(pack_key(heap_.top().key.first, heap_.top().key.second));  // overlaps the miss with the sift-down
     BPEHeapEntry top = heap_.pop();
     const uint64_t k = pack_key(top.key.first, top.key.second);
     uint32_t* vp = version_.find(k);
@@ -275,6 +277,12 @@ int TrainerCore::train() {  // bpe.cpp:345-386
   train_wall_ms_ = now_ms() - t0;
   merges_last_ = static_cast<uint64_t>(total);
   if (!quiet_) std::printf("[INFO]\t Training completed. Performed %d merges\n", total);
+  if (const char* dbg = std::getenv("SHRED_DEBUG_TIMING")) if (*dbg && *dbg != '0') {
+    EngineStats es; std::memset(&es, 0, sizeof es); eng_->stats(&es);
+    std::fprintf(stderr, "[TIMING]\t train %.1f ms (device %.1f): engine.merge %.1f (launch %.1f, wait %.1f), host heap %.1f, merges %d, pushes %llu pops %llu\n",
+                 train_wall_ms_, train_device_ms_, es.merge_ms, es.launch_ms, es.wait_ms, host_heap_ms_, total,
+                 static_cast<unsigned long long>(heap_.pushes), static_cast<unsigned long long>(heap_.pops));
+  }
   sync_mirrors();
   return total;
 }
