@@ -173,7 +173,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["SHRED_QUIET"] = "1"
-    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "16")  # CUDA events around every 16th merge scan
+    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "8")  # CUDA events around every 8th merge scan
     os.environ["SHRED_DEVICE"] = str(local_rank)
     import __graft_entry__ as ge
     if rank == 0:
@@ -238,9 +238,13 @@ def main():
         train_dev_ms, e2e_s, wall = tt.tolist()
     total_merges = merges * args.steps * world
     st = steps[-1][3]
-    scan_ms = sum(s[3]["scan_device_ms"] for s in steps)
-    scan_bytes = sum(s[3]["scan_bytes"] for s in steps)
-    scan_n = sum(s[3]["scan_launches"] for s in steps)
+    all_ms = sum(s[3]["scan_device_ms"] for s in steps)
+    all_bytes = sum(s[3]["scan_bytes"] for s in steps)
+    all_touched = sum(s[3]["scan_bytes_touched"] for s in steps)
+    all_n = sum(s[3]["scan_launches"] for s in steps)
+    scan_ms = sum(s[3]["dense_device_ms"] for s in steps)
+    scan_bytes = sum(s[3]["dense_bytes"] for s in steps)
+    scan_n = sum(s[3]["dense_launches"] for s in steps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -259,7 +263,14 @@ def main():
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "launches_timed": int(scan_n), "avg_launch_us": 1e3 * scan_ms / scan_n if scan_n else None,
-                     "bytes_per_launch": scan_bytes / scan_n if scan_n else None},
+                     "bytes_per_launch": scan_bytes / scan_n if scan_n else None,
+                     "note": "achieved/frac = timed k_scan_merge launches that streamed >= 90 % of the symbol array (no tile skipped): 4*slots bytes / CUDA-event "
+                             "duration, which includes the kernel's delta emission and last-CTA finalize tail; 'all_launches' = every timed launch incl. tile-skipping ones "
+                             "(effective = algorithmic 4*slots bytes / duration, touched = bytes of candidate tiles actually read / duration)",
+                     "all_launches": {"n": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
+                                      "effective_gbs": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else None,
+                                      "touched_gbs": all_touched / (all_ms * 1e-3) / 1e9 if all_ms else None,
+                                      "tiles_scanned_frac": st["cand_tiles"] / st["tiles_total"] if st["tiles_total"] else None}},
         "detail": {"merges_per_step": merges, "n_words": int(st["n_words"]), "n_symbols_initial": int(st["n_symbols_initial"]), "n_symbols_final": int(st["n_symbols_live"]),
                    "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
                    "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],

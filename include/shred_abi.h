@@ -111,6 +111,9 @@ typedef struct shred_stats_t {
   double load_wall_ms, h2d_ms, train_wall_ms, host_heap_ms, wait_ms, save_wall_ms;
   double train_device_ms;        /* CUDA-event time of the last bpe_train on the engine's stream */
   double launch_ms;              /* host time spent issuing the per-merge kernel launches */
+  double scan_bytes_touched;     /* bytes of the symbol array the timed scans actually read (candidate tiles) */
+  uint64_t dense_launches; double dense_device_ms; double dense_bytes; /* timed scans that streamed >= 90 % of the array */
+  uint64_t cand_tiles, tiles_total; /* candidate / total tiles summed over all merges of the last train */
   uint64_t h2d_bytes, d2h_bytes;
 } shred_stats_t;
 SHRED_API int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);

@@ -17,9 +17,9 @@
 //   k_scatter/k_rank .. hash.cpp:61-72                     word order = (djb2 & 4095, first occurrence)
 //   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids with unk substitution
 //   k_count ........... bpe.cpp:187-218                    adjacent pair counts
-//   k_scan_merge ...... bpe.cpp:265-290,297-318            HBM-bound scan for the chosen pair, per-occurrence count deltas,
-//                                                          last block folds them into the pair table and publishes records
-//   k_rewrite ......... bpe.cpp:291-296                    in-place left-packed rewrite of the touched words
+//   k_merge ........... bpe.cpp:265-318                    one cooperative launch per merge: HBM-bound scan of the candidate tiles
+//                                                          with per-occurrence count deltas | grid barrier | deltas folded into the
+//                                                          pair table + records published | in-place rewrite of the touched words
 //   k_token_freq ...... bpe.cpp:409-415                    final token frequencies
 #include <cuda_runtime.h>
 
@@ -61,7 +61,7 @@ constexpr uint64_t PT_EMPTY = ~0ull;
 constexpr uint64_t SEQ_MAX = ~0ull;
 constexpr int N_SM_FALLBACK = 148;
 
-enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32 };
+enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32, ERR_BARRIER = 64 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -74,7 +74,7 @@ __device__ __forceinline__ uint64_t fc_key(int32_t a, int32_t b) {  // bpe.cpp:2
 
 struct Ctrl {  // mapped pinned host memory, written by finalize_block
   volatile uint64_t flag;
-  uint64_t n_recs, occ, pt_n, n_leaders, n_keys;
+  uint64_t n_recs, occ, pt_n, n_leaders, n_keys, cand_tiles;
   uint32_t err, pad;
 };
 
@@ -85,14 +85,16 @@ struct DevCounters {  // device memory
   uint32_t err, pad;
   ull n_tokens;
   uint32_t n_unique, blocks_done2;
+  uint32_t cand_tiles, bar;
 };
 
 struct DeltaTable {
-  uint64_t* keys; ull* delta; ull* seq; uint32_t* list;
+  uint64_t* keys; ull* delta; ull* seq; uint32_t* list; uint64_t* klist;  // list/klist: slot and key of every used slot, dense
   uint64_t mask; uint64_t empty; uint32_t cap;
 };
+struct PairEnt { uint64_t key; uint64_t freq; };  // one 16-byte load fetches both
 struct PairTable {
-  uint64_t* keys; ull* freq;
+  PairEnt* ent;
   uint64_t mask; uint64_t cap;
 };
 
@@ -106,7 +108,7 @@ __device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, u
       uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot]), static_cast<ull>(dt.empty), static_cast<ull>(key));
       if (prev == dt.empty) {
         uint32_t idx = atomicAdd(&ctr->dt_n, 1u);
-        if (idx < dt.cap) dt.list[idx] = static_cast<uint32_t>(slot);
+        if (idx < dt.cap) { dt.list[idx] = static_cast<uint32_t>(slot); dt.klist[idx] = key; }
         cur = key;
       } else cur = prev;
     }
@@ -120,20 +122,27 @@ __device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, u
   atomicOr(&ctr->err, ERR_DT_FULL);
 }
 
-// returns the slot of `key`, inserting it with freq 0 if absent
-__device__ __forceinline__ uint64_t pt_slot(const PairTable& pt, DevCounters* ctr, uint64_t key) {
+__device__ __forceinline__ ull gtime() { ull t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ ulonglong2 ld_ent(const PairEnt* e) { return *reinterpret_cast<const ulonglong2*>(e); }
+
+// Finds `key` (inserting it if absent) and returns its slot; *old_freq = its frequency (0 for a new entry).
+// `first` is the already-loaded entry at the home slot (lets the caller issue several home loads back to back).
+// Only finalize_block calls this, with distinct keys per pass, so a claimed entry has exactly one writer.
+__device__ __forceinline__ uint64_t pt_find_or_insert(const PairTable& pt, DevCounters* ctr, uint64_t key, ulonglong2 first, uint64_t* old_freq) {
   uint64_t slot = mix64(key) & pt.mask;
+  ulonglong2 e = first;
   for (uint64_t probe = 0; probe < pt.cap; ++probe) {
-    uint64_t cur = pt.keys[slot];
-    if (cur == PT_EMPTY) {
-      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.keys[slot]), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
-      if (prev == PT_EMPTY) { atomicAdd(&ctr->pt_n, 1ull); return slot; }
-      cur = prev;
+    if (e.x == key) { *old_freq = e.y; return slot; }
+    if (e.x == PT_EMPTY) {
+      const uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
+      if (prev == PT_EMPTY) { atomicAdd(&ctr->pt_n, 1ull); *old_freq = 0; return slot; }
+      if (prev == key) { *old_freq = pt.ent[slot].freq; return slot; }
     }
-    if (cur == key) return slot;
     slot = (slot + 1) & pt.mask;
+    e = ld_ent(&pt.ent[slot]);
   }
   atomicOr(&ctr->err, ERR_PT_FULL);
+  *old_freq = 0;
   return 0;
 }
 
@@ -382,57 +391,106 @@ __global__ void __launch_bounds__(256) k_count(const int32_t* __restrict__ ids, 
 
 // -------------------------------------------------------------------------------------------------------------- merge
 
+// ---- tile occurrence index ------------------------------------------------------------------------------------
+// planes[id * W + (t >> 5)] bit (t & 31) is set if token `id` occurs in slots [1024 t, 1024 t + 1024] (the first slot of
+// the next tile included, so a pair that straddles the boundary is found from tile t).  Bits are only ever added between
+// two compactions, so the index is a superset of the truth: a merge scans exactly the tiles whose bit is set for both A
+// and B and provably misses nothing.  Late merges touch a few hundred of tens of thousands of tiles.
+constexpr uint32_t TILE_SHIFT = 10, TILE_SLOTS = 1u << TILE_SHIFT, TILE_I4 = TILE_SLOTS / 4, MAX_TILES_PER_CTA = 1024;
+static_assert(TILE_I4 % (32 * 4) == 0, "a tile is a whole number of warp chunks");
+
+__device__ __forceinline__ void plane_set(uint32_t* planes, uint32_t W, uint32_t id_cap, int32_t id, uint64_t slot) {
+  if (id < 0 || static_cast<uint32_t>(id) >= id_cap) return;
+  uint32_t t = static_cast<uint32_t>(slot >> TILE_SHIFT);
+  uint32_t* wp = planes + static_cast<uint64_t>(id) * W + (t >> 5);
+  uint32_t bit = 1u << (t & 31);
+  if (!(*wp & bit)) atomicOr(wp, bit);
+  if ((slot & (TILE_SLOTS - 1)) == 0 && t > 0) {
+    --t;
+    wp = planes + static_cast<uint64_t>(id) * W + (t >> 5);
+    bit = 1u << (t & 31);
+    if (!(*wp & bit)) atomicOr(wp, bit);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_build_planes(const int32_t* __restrict__ ids, uint64_t n_slots, uint32_t* planes, uint32_t W, uint32_t id_cap) {
+  for (uint64_t p = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; p < n_slots; p += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    plane_set(planes, W, id_cap, ids[p], p);
+}
+
 // Shared by the count pass (COUNT=true, bpe.cpp:219-227) and the merge pass (bpe.cpp:297-318): fold the aggregated deltas
 // into the pair table and write one record per touched key for the host.  Runs in ONE block (any size): the stand-alone
 // k_finalize_count kernel, or the last block of k_scan_merge to finish.  Ends by publishing the counters to the host and
 // re-arming them.
 template <bool COUNT>
 __device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
-                                               int32_t A, int32_t B, const Params& P, uint64_t flag_value) {
+                                               int32_t A, int32_t B, const Params& P, uint64_t flag_value, ull* dbg = nullptr) {
+  __shared__ uint32_t s_rec_n;
+  if (dbg && threadIdx.x == 0) dbg[2] = gtime();
+  constexpr int ILP = 4;  // keys in flight per thread: the pass is a chain of dependent DRAM/L2 round trips
   const uint32_t n = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
-  if (!COUNT && threadIdx.x == blockDim.x - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
-    const uint64_t s = pt_slot(pt, ctr, fc_key(A, B));
-    pt.freq[s] = 0ull;
-  }
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint32_t ds = dt.list[i];
-    const uint64_t key = dt.keys[ds];
-    const int64_t d = static_cast<int64_t>(dt.delta[ds]);
-    const uint64_t seq = dt.seq[ds];
-    dt.keys[ds] = dt.empty; dt.delta[ds] = 0ull; dt.seq[ds] = SEQ_MAX;
-    const int32_t pa = static_cast<int32_t>(key >> 32), pb = static_cast<int32_t>(key & 0xFFFFFFFFu);  // bpe.cpp:301
-    Rec out; out.key = key; out.seq = seq; out.pad = 0;
-    bool emit = false;
-    if (!COUNT && pa == A && pb == B) continue;  // bpe.cpp:302
-    if (!COUNT && (pa == P.unk_id || pb == P.unk_id)) {  // phantom pair: tracked by the host (Appendix A12)
-      out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d); emit = true;
-    } else {
-      const uint64_t s = pt_slot(pt, ctr, key);
-      const uint64_t old = pt.freq[s];
-      uint64_t nf;
-      if (d < 0) { const uint64_t ad = static_cast<uint64_t>(-d); nf = old >= ad ? old - ad : 0; } else nf = old + static_cast<uint64_t>(d);  // bpe.cpp:303-307
-      pt.freq[s] = nf;
-      if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
-      else if (!COUNT && old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
-    }
-    if (emit) {
-      const uint32_t idx = atomicAdd(&ctr->rec_n, 1u);
-      if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
-    }
-  }
-  __threadfence_system();
+  if (threadIdx.x == 0) s_rec_n = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    ctrl->n_recs = ctr->rec_n < rec_cap ? ctr->rec_n : rec_cap;
+  if (!COUNT && threadIdx.x == blockDim.x - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
+    const uint64_t k = fc_key(A, B);
+    uint64_t old;
+    const uint64_t s = pt_find_or_insert(pt, ctr, k, ld_ent(&pt.ent[mix64(k) & pt.mask]), &old);
+    pt.ent[s].freq = 0ull;
+  }
+  for (uint32_t base = 0; base < n; base += blockDim.x * ILP) {
+    uint64_t key[ILP]; uint32_t ds[ILP]; ulonglong2 home[ILP]; int64_t d[ILP]; uint64_t sq[ILP]; bool ok[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+      const uint32_t i = base + j * blockDim.x + threadIdx.x;
+      ok[j] = i < n;
+      if (ok[j]) { key[j] = dt.klist[i]; ds[j] = dt.list[i]; }
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; j++) if (ok[j]) {
+      home[j] = ld_ent(&pt.ent[mix64(key[j]) & pt.mask]);
+      d[j] = static_cast<int64_t>(dt.delta[ds[j]]);
+      sq[j] = dt.seq[ds[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; j++) if (ok[j]) {
+      dt.keys[ds[j]] = dt.empty; dt.delta[ds[j]] = 0ull; dt.seq[ds[j]] = SEQ_MAX;  // re-arm the scratch slot
+      const int32_t pa = static_cast<int32_t>(key[j] >> 32), pb = static_cast<int32_t>(key[j] & 0xFFFFFFFFu);  // bpe.cpp:301
+      Rec out; out.key = key[j]; out.seq = sq[j]; out.pad = 0; out.kind = REC_PUSH; out.val = 0;
+      bool emit = false;
+      if (!COUNT && pa == A && pb == B) continue;  // bpe.cpp:302
+      if (!COUNT && (pa == P.unk_id || pb == P.unk_id)) {  // phantom pair: tracked by the host (Appendix A12)
+        out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d[j]); emit = true;
+      } else {
+        uint64_t old;
+        const uint64_t s = pt_find_or_insert(pt, ctr, key[j], home[j], &old);
+        uint64_t nf;
+        if (d[j] < 0) { const uint64_t ad = static_cast<uint64_t>(-d[j]); nf = old >= ad ? old - ad : 0; } else nf = old + static_cast<uint64_t>(d[j]);  // bpe.cpp:303-307
+        pt.ent[s].freq = nf;
+        if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
+        else if (!COUNT && old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
+      }
+      if (emit) {
+        const uint32_t idx = atomicAdd(&s_rec_n, 1u);
+        if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
+      }
+    }
+  }
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[3] = gtime();
+  if (threadIdx.x == 0) {  // counters for the host, then re-arm them for the next pass
+    ctrl->n_recs = s_rec_n < rec_cap ? s_rec_n : rec_cap;
     ctrl->occ = ctr->occ;
     ctrl->pt_n = ctr->pt_n;
     ctrl->n_leaders = ctr->wl_n;
     ctrl->n_keys = ctr->dt_n;
+    ctrl->cand_tiles = ctr->cand_tiles;
     ctrl->err = ctr->err;
-    ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->occ = 0ull;
-    __threadfence_system();
-    ctrl->flag = flag_value;
+    ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->occ = 0ull; ctr->cand_tiles = 0;
   }
+  __threadfence_system();  // every thread's records (and thread 0's counters) are visible to the host ...
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[4] = gtime();
+  if (threadIdx.x == 0) ctrl->flag = flag_value;  // ... before the flag it spins on
 }
 
 __global__ void __launch_bounds__(256) k_finalize_count(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
@@ -443,7 +501,7 @@ __global__ void __launch_bounds__(256) k_finalize_count(DeltaTable dt, PairTable
 // One occurrence of (A,B) at flat position p: the four count deltas of bpe.cpp:274-290, computed independently per
 // occurrence.  Left neighbour = the id that stands there when the reference's left-to-right pass reaches p (N if the two
 // symbols before p were themselves merged in this pass), right neighbour = the raw id two slots on.
-__device__ __forceinline__ void emit_occurrence(const int32_t* __restrict__ ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
+__device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
                                                 int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
                                                 uint32_t& my_occ) {
   const int32_t l1 = ids[p - 1];
@@ -474,70 +532,160 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* __restrict__ ids,
   ++my_occ;
 }
 
-// The per-merge pass.  HBM-bound scan: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs that start
-// in it; an occurrence emits its count deltas straight into the delta table and is remembered for the rewrite kernel.
-// The last block to finish folds the deltas into the pair table and publishes the records to the host (finalize_block),
-// so the host can replay its heap while k_rewrite is still running.
-template <int UNROLL>
-__global__ void __launch_bounds__(256) k_scan_merge(const int4* __restrict__ ids4, uint32_t n4, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
-                                                    int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt, DevCounters* ctr,
-                                                    uint32_t* __restrict__ ml, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, uint64_t flag_value) {
-  const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  constexpr uint32_t CHUNK = 32u * UNROLL;
-  uint32_t my_occ = 0;
-  for (uint64_t base = static_cast<uint64_t>(warp) * CHUNK; base < n4; base += static_cast<uint64_t>(n_warps) * CHUNK) {
-    int4 v[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const uint64_t i = base + u * 32u + lane;
-      v[u] = i < n4 ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+// Software grid barrier for the cooperative per-merge kernel (all CTAs are co-resident: cudaLaunchCooperativeKernel).
+// `bar` only ever grows; `target` = value it reaches when every CTA of this launch has arrived at this barrier.
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uint32_t* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(*reinterpret_cast<volatile uint32_t*>(bar) - target) < 0) {
+      if (clock64() - t0 > 4000000000ll) { atomicOr(err, ERR_BARRIER); break; }  // ~2 s: never hang the GPU on a host-side accounting bug
     }
-    int32_t after = DEAD;  // first symbol after this chunk (needed by lane 31 of the last row)
-    if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldg(ids + 4 * i); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// The per-merge kernel (cooperative launch, persistent grid = SM count x resident CTAs).
+//   phase 1  HBM-bound scan of the candidate tiles: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs
+//            that start in it; an occurrence emits its count deltas straight into the delta table and is remembered
+//   barrier
+//   phase 2  every thread folds a share of the touched keys into the pair table and writes the records (bpe.cpp:297-318);
+//            the last CTA to finish publishes the counters and the flag the host spins on
+//   phase 3  in-place left-packed rewrite of the touched words (bpe.cpp:291-296), off the host's critical path: the
+//            first occurrence to claim a word (claimed[wi] = merge number) rewrites it; the last CTA re-arms the counters
+template <int UNROLL>
+__global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint32_t n_tiles, uint32_t tiles_per_cta,
+                                               const uint32_t* __restrict__ planeA, const uint32_t* __restrict__ planeB, uint32_t* planes, uint32_t W, uint32_t id_cap,
+                                               const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, const ull* __restrict__ woff, uint32_t* wlen,
+                                               uint32_t* claimed, uint32_t merge_no, int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt,
+                                               DevCounters* ctr, uint32_t* __restrict__ ml, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, uint64_t flag_value,
+                                               uint32_t bar_target, ull* dbg) {
+  __shared__ uint32_t cand[MAX_TILES_PER_CTA];
+  __shared__ uint32_t n_cand;
+  __shared__ bool last;
+  int32_t* ids = reinterpret_cast<int32_t*>(ids4);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  constexpr uint32_t CHUNK = 32u * UNROLL;
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[0] = gtime();
+  // ---- phase 1: this CTA's contiguous tile range -> candidate tiles (both tokens present); no planes = every tile
+  const uint32_t t0 = blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, n_tiles);
+  uint32_t my_occ = 0, nc_total = 0;
+  for (uint32_t ts = t0; ts < t1; ts += MAX_TILES_PER_CTA) {  // (one round unless the array exceeds ~900 M slots)
+  const uint32_t te_round = min(ts + MAX_TILES_PER_CTA, t1);
+  __syncthreads();
+  if (threadIdx.x == 0) n_cand = 0;
+  __syncthreads();
+  for (uint32_t t = ts + threadIdx.x; t < te_round; t += blockDim.x) {
+    const bool c = planeA == nullptr || (((planeA[t >> 5] & planeB[t >> 5]) >> (t & 31)) & 1u);
+    if (c) cand[atomicAdd(&n_cand, 1u)] = t;
+  }
+  __syncthreads();
+  const uint32_t nc = n_cand;
+  nc_total += nc;
+  for (uint32_t ci = warp; ci < nc; ci += warps) {
+    const uint64_t tb = static_cast<uint64_t>(cand[ci]) * TILE_I4;
+    const uint64_t te = min(tb + TILE_I4, static_cast<uint64_t>(n4));
+    for (uint64_t base = tb; base < te; base += CHUNK) {
+      int4 v[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
-      const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
-      if (lane == 31) nxt = row_next;
-      uint32_t m = 0;
-      m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
-      m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
-      m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
-      m |= (v[u].w == A && nxt == B) ? 8u : 0u;
-      if (__any_sync(0xFFFFFFFFu, m != 0)) {
-        const uint64_t p0 = (base + u * 32u + lane) * 4u;
-        while (m) {
-          const int k = __ffs(m) - 1;
-          m &= m - 1;
-          emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ);
+      for (int u = 0; u < UNROLL; u++) {
+        const uint64_t i = base + u * 32u + lane;
+        v[u] = i < n4 ? __ldcv(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+      }
+      int32_t after = DEAD;  // first symbol after this chunk (needed by lane 31 of the last row)
+      if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldcv(ids + 4 * i); }
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
+        const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
+        if (lane == 31) nxt = row_next;
+        uint32_t m = 0;
+        m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
+        m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
+        m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
+        m |= (v[u].w == A && nxt == B) ? 8u : 0u;
+        if (__any_sync(0xFFFFFFFFu, m != 0)) {
+          const uint64_t p0 = (base + u * 32u + lane) * 4u;
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ);
+          }
         }
       }
     }
   }
+  }
   for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
   if (lane == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
-  // last block out folds the deltas and publishes
-  __shared__ bool last;
+  if (threadIdx.x == 0 && nc_total) atomicAdd(&ctr->cand_tiles, nc_total);
+  grid_barrier(&ctr->bar, bar_target, &ctr->err);
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[1] = gtime();
+
+  // ---- phase 2: fold the aggregated deltas into the pair table, one key per thread
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t n_keys = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
+  if (gtid == gthreads - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
+    const uint64_t k = fc_key(A, B);
+    uint64_t old;
+    const uint64_t sl = pt_find_or_insert(pt, ctr, k, ld_ent(&pt.ent[mix64(k) & pt.mask]), &old);
+    pt.ent[sl].freq = 0ull;
+  }
+  bool wrote = false;
+  for (uint32_t i = gtid; i < n_keys; i += gthreads) {
+    const uint64_t key = dt.klist[i];
+    const uint32_t ds = dt.list[i];
+    const ulonglong2 home = ld_ent(&pt.ent[mix64(key) & pt.mask]);
+    const int64_t d = static_cast<int64_t>(dt.delta[ds]);
+    const uint64_t sq = dt.seq[ds];
+    dt.keys[ds] = dt.empty; dt.delta[ds] = 0ull; dt.seq[ds] = SEQ_MAX;  // re-arm the scratch slot
+    const int32_t pa = static_cast<int32_t>(key >> 32), pb = static_cast<int32_t>(key & 0xFFFFFFFFu);  // bpe.cpp:301
+    if (pa == A && pb == B) continue;  // bpe.cpp:302
+    Rec out; out.key = key; out.seq = sq; out.pad = 0; out.kind = REC_PUSH; out.val = 0;
+    bool emit = false;
+    if (pa == P.unk_id || pb == P.unk_id) {  // phantom pair: tracked by the host (Appendix A12)
+      out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d); emit = true;
+    } else {
+      uint64_t old;
+      const uint64_t sl = pt_find_or_insert(pt, ctr, key, home, &old);
+      uint64_t nf;
+      if (d < 0) { const uint64_t ad = static_cast<uint64_t>(-d); nf = old >= ad ? old - ad : 0; } else nf = old + static_cast<uint64_t>(d);  // bpe.cpp:303-307
+      pt.ent[sl].freq = nf;
+      if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
+      else if (old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
+    }
+    if (emit) {
+      const uint32_t idx = atomicAdd(&ctr->rec_n, 1u);
+      if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
+      wrote = true;
+    }
+  }
+  if (wrote) __threadfence_system();  // my records are visible to the host before I count myself done
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (last) {
+  if (last && threadIdx.x == 0) {  // publish
     __threadfence();
-    finalize_block<false>(dt, pt, ctr, recs, rec_cap, ctrl, A, B, P, flag_value);
+    const uint32_t nr = *reinterpret_cast<volatile uint32_t*>(&ctr->rec_n);
+    ctrl->n_recs = nr < rec_cap ? nr : rec_cap;
+    ctrl->occ = *reinterpret_cast<volatile ull*>(&ctr->occ);
+    ctrl->pt_n = *reinterpret_cast<volatile ull*>(&ctr->pt_n);
+    ctrl->n_leaders = *reinterpret_cast<volatile uint32_t*>(&ctr->wl_n);
+    ctrl->n_keys = n_keys;
+    ctrl->cand_tiles = *reinterpret_cast<volatile uint32_t*>(&ctr->cand_tiles);
+    ctrl->err = *reinterpret_cast<volatile uint32_t*>(&ctr->err);
+    __threadfence_system();
+    ctrl->flag = flag_value;
+    if (dbg) dbg[2] = gtime();
   }
-}
 
-// Rewrites every word that holds an occurrence: the reference's left-to-right relink (bpe.cpp:268-296) as an in-place,
-// left-packed rewrite of the word's slot.  The first occurrence to claim the word (claimed[wi] = merge number) does it.
-__global__ void __launch_bounds__(128) k_rewrite(int32_t* ids, const uint32_t* __restrict__ wid, const ull* __restrict__ woff, uint32_t* wlen,
-                                                 uint32_t* claimed, const uint32_t* __restrict__ ml, int32_t A, int32_t B, int32_t N, uint32_t merge_no,
-                                                 DevCounters* ctr) {
-  const uint32_t n = ctr->wl_n;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  // ---- phase 3: rewrite the touched words in place (left-packed); the host is already replaying its heap
+  const uint32_t n_match = ctr->wl_n;
+  for (uint32_t i = gtid; i < n_match; i += gthreads) {
     const uint32_t wi = wid[ml[i]];
     if (atomicMax(&claimed[wi], merge_no) >= merge_no) continue;
     const uint64_t q = woff[wi] + 1;
@@ -550,10 +698,11 @@ __global__ void __launch_bounds__(128) k_rewrite(int32_t* ids, const uint32_t* _
       if (cur == A && nxt == B) {
         const int32_t nn = ids[r + 2];
         ids[w] = N;
+        if (planes) plane_set(planes, W, id_cap, N, w);
         ++w; r += 2;
         cur = nn;
       } else {
-        if (w != r) ids[w] = cur;
+        if (w != r) { ids[w] = cur; if (planes) plane_set(planes, W, id_cap, cur, w); }  // a moved symbol may enter another tile
         ++w; ++r;
         cur = nxt;
       }
@@ -561,22 +710,23 @@ __global__ void __launch_bounds__(128) k_rewrite(int32_t* ids, const uint32_t* _
     for (uint64_t k = w; k < r; k++) ids[k] = DEAD;
     wlen[wi] = static_cast<uint32_t>(w - q);
   }
-  // last block re-arms the match counter for the next merge
-  __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done2, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (last && threadIdx.x == 0) { ctr->wl_n = 0; ctr->blocks_done2 = 0; }
+  if (last && threadIdx.x == 0) {  // every CTA has read the counters: re-arm them for the next merge
+    ctr->wl_n = 0; ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->blocks_done2 = 0; ctr->occ = 0ull; ctr->cand_tiles = 0;
+    if (dbg) dbg[3] = gtime();
+  }
 }
 
 __global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {
   for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < oldt.cap; s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t k = oldt.keys[s];
-    if (k == PT_EMPTY) continue;
-    uint64_t slot = mix64(k) & newt.mask;
+    const ulonglong2 e = ld_ent(&oldt.ent[s]);
+    if (e.x == PT_EMPTY) continue;
+    uint64_t slot = mix64(e.x) & newt.mask;
     for (;;) {
-      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&newt.keys[slot]), static_cast<ull>(PT_EMPTY), static_cast<ull>(k));
-      if (prev == PT_EMPTY) { newt.freq[slot] = oldt.freq[s]; break; }
+      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&newt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(e.x));
+      if (prev == PT_EMPTY) { newt.ent[slot].freq = e.y; break; }
       slot = (slot + 1) & newt.mask;
     }
   }
@@ -634,8 +784,13 @@ class CudaEngine : public Engine {
     CK(cudaEventCreate(&evm1_));
     cudaMemPool_t pool;  // stream-ordered allocations; keep freed blocks cached so repeated loads do not pay cudaMalloc
     if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+    if (const char* d = std::getenv("SHRED_DEBUG_TIMING")) if (*d && *d != '0') {
+      void* dp = nullptr;
+      CK(cudaHostAlloc(&dp, 8 * sizeof(ull), cudaHostAllocMapped));
+      dbg_ = static_cast<ull*>(dp);
+    }
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_merge<4>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     return 0;
@@ -689,6 +844,7 @@ class CudaEngine : public Engine {
       wt.cap = cap; wt.mask = cap - 1;
       CK(cudaMemsetAsync(wt.tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt.first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt.count, 0, cap * 8, st_));
       CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
+      bar_count_ = 0;
       if (n) { k_tokenize<<<grid_for((n + 15) / 16, 256), 256, 0, st_>>>(d_text, n, wt, ctr_, seed); launches_++; es_.ingest_launches++; }
       DevCounters c;
       CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
@@ -770,9 +926,29 @@ class CudaEngine : public Engine {
     CK(cudaStreamSynchronize(st_));
     CK(cudaGetLastError());
     free_tmp(); free_wt();
+    RC(build_planes());
     // --- pair/delta tables sized for this trainer
     RC(alloc_tables());
     loaded_ = true;
+    return 0;
+  }
+
+  // (re)build the tile occurrence index for the current ids buffer
+  int build_planes() {
+    if (std::getenv("SHRED_NO_TILE_INDEX")) return 0;
+    const uint32_t n_tiles_cap = static_cast<uint32_t>((ids_cap_ + TILE_SLOTS - 1) >> TILE_SHIFT);
+    const uint32_t W = (n_tiles_cap + 31) / 32;
+    const uint32_t id_cap = static_cast<uint32_t>(256 + vocab_hint_ + 64);
+    const uint64_t bytes = static_cast<uint64_t>(id_cap) * W * 4;
+    if (!planes_ || W != plane_words_ || id_cap != id_cap_) {
+      if (planes_) { cudaFreeAsync(planes_, st_); planes_ = nullptr; }
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 3) { plane_words_ = 0; id_cap_ = 0; return 0; }  // too big: scan every tile
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&planes_), bytes, st_));
+      plane_words_ = W; id_cap_ = id_cap;
+    }
+    CK(cudaMemsetAsync(planes_, 0, bytes, st_));
+    if (n_slots_) { k_build_planes<<<grid_for(n_slots_, 256), 256, 0, st_>>>(ids_[cur_], n_slots_, planes_, plane_words_, id_cap_); launches_++; }
     return 0;
   }
 
@@ -781,7 +957,7 @@ class CudaEngine : public Engine {
       uint64_t cap = next_pow2(8ull * (256 + vocab_hint_) + 1024); if (cap < (1u << 16)) cap = 1u << 16;
       RC(alloc_dt(cap));
     }
-    if (!pt_.keys) RC(alloc_pt(&pt_, 1ull << 20));
+    if (!pt_.ent) RC(alloc_pt(&pt_, 1ull << 20));
     if (!recs_) {
       rec_cap_ = dt_.cap;
       CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped));
@@ -789,9 +965,10 @@ class CudaEngine : public Engine {
     return 0;
   }
   int alloc_dt(uint64_t cap) {
-    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); dt_.keys = nullptr; }
+    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); dt_.keys = nullptr; }
     CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.keys), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.delta), cap * 8, st_));
     CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.seq), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.list), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.klist), cap * 8, st_));
     dt_.cap = static_cast<uint32_t>(cap); dt_.mask = cap - 1;
     // a key value no pair can produce: high word >= 2^31 that is neither all-ones nor unk_id
     uint32_t hi = 0x80000000u; if (static_cast<uint32_t>(cfg_.unk_id) == hi) hi = 0x80000001u;
@@ -803,9 +980,9 @@ class CudaEngine : public Engine {
     return 0;
   }
   int alloc_pt(PairTable* pt, uint64_t cap) {
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->keys), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->freq), cap * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->ent), cap * sizeof(PairEnt), st_));
     pt->cap = cap; pt->mask = cap - 1;
-    CK(cudaMemsetAsync(pt->keys, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(pt->freq, 0, cap * 8, st_));
+    CK(cudaMemsetAsync(pt->ent, 0xFF, cap * sizeof(PairEnt), st_));  // key = EMPTY; freq is written when the entry is claimed
     return 0;
   }
   int grow_pt(uint64_t need_entries) {
@@ -815,7 +992,7 @@ class CudaEngine : public Engine {
     RC(alloc_pt(&nt, cap));
     k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
     CK(cudaStreamSynchronize(st_));
-    cudaFreeAsync(pt_.keys, st_); cudaFreeAsync(pt_.freq, st_);
+    cudaFreeAsync(pt_.ent, st_);
     pt_ = nt;
     return 0;
   }
@@ -826,8 +1003,9 @@ class CudaEngine : public Engine {
     *recs = recs_; *n = 0;
     if (!loaded_) return 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
-      CK(cudaMemsetAsync(pt_.keys, 0xFF, pt_.cap * 8, st_)); CK(cudaMemsetAsync(pt_.freq, 0, pt_.cap * 8, st_));
+      CK(cudaMemsetAsync(pt_.ent, 0xFF, pt_.cap * sizeof(PairEnt), st_));
       CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
+      bar_count_ = 0;
       pt_n_ = 0;
       ++flag_;
       CK(cudaEventRecord(ev0_, st_));
@@ -872,20 +1050,49 @@ class CudaEngine : public Engine {
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
     if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
-    k_scan_merge<4><<<detect_grid(n4), 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_[cur_]), n4, wid_[cur_], wcnt_, a, b, new_id, P_, dt_, pt_, ctr_, wl_,
-                                                       recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), flag_);
+    if (dbg_) { dbg_[0] = dbg_[1] = dbg_[2] = dbg_[3] = dbg_[4] = 0; }
+    const double th0 = now_ms();
+    const uint32_t n_tiles = static_cast<uint32_t>((n_slots_ + TILE_SLOTS - 1) >> TILE_SHIFT);
+    int grid = detect_grid(n4);
+    const uint32_t tiles_per_cta = (n_tiles + grid - 1) / grid;
+    const bool indexed = planes_ && static_cast<uint32_t>(a) < id_cap_ && static_cast<uint32_t>(b) < id_cap_;
+    const uint32_t* pa = indexed ? planes_ + static_cast<uint64_t>(a) * plane_words_ : nullptr;
+    const uint32_t* pb = indexed ? planes_ + static_cast<uint64_t>(b) * plane_words_ : nullptr;
+    {
+      int4* a_ids = reinterpret_cast<int4*>(ids_[cur_]);
+      uint32_t a_n4 = n4, a_nt = n_tiles, a_tpc = tiles_per_cta, a_W = plane_words_, a_idcap = id_cap_, a_mno = merge_no_, a_reccap = rec_cap_;
+      const uint32_t* a_wid = wid_[cur_]; const ull* a_wcnt = wcnt_; const ull* a_woff = woff_[cur_];
+      int32_t a_A = a, a_B = b, a_N = new_id;
+      Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
+      uint64_t a_flag = flag_;
+      bar_count_ += static_cast<uint32_t>(grid);  // one grid barrier per launch; the counter only grows (wraps mod 2^32)
+      uint32_t a_bar = bar_count_;
+      void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
+                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &dbg_};
+      CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_merge<4>), dim3(grid), dim3(256), args, 0, st_));
+    }
     if (timed) CK(cudaEventRecord(ev1_, st_));
-    k_rewrite<<<n_sm_, 128, 0, st_>>>(ids_[cur_], wid_[cur_], woff_[cur_], wlen_, claimed_, wl_, a, b, new_id, merge_no_, ctr_);
-    launches_ += 2;
+    launches_ += 1;
     launch_ms_ += now_ms() - tl0;
     RC(wait_flag());
+    if (dbg_) {
+      cudaStreamSynchronize(st_);
+      dbg_acc_[0] += (dbg_[1] - dbg_[0]) * 1e-3; dbg_acc_[1] += (dbg_[2] - dbg_[1]) * 1e-3; dbg_acc_[2] += (dbg_[3] - dbg_[2]) * 1e-3;
+      dbg_acc_[4] += (now_ms() - th0) * 1e3; dbg_n_++;
+      if ((dbg_n_ % 2000) == 0 || dbg_n_ == 50)
+        std::fprintf(stderr, "[KTIME]\t merges %llu: scan+emit+barrier %.1f us, finalize+publish %.1f us, rewrite+rearm %.1f us | host launch->kernel end %.1f us (avg per merge)\n",
+                     (unsigned long long)dbg_n_, dbg_acc_[0] / dbg_n_, dbg_acc_[1] / dbg_n_, dbg_acc_[2] / dbg_n_, dbg_acc_[4] / dbg_n_);
+    }
     if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
     if (timed) {
       float ms = 0;
       CK(cudaEventSynchronize(ev1_));
       cudaEventElapsedTime(&ms, ev0_, ev1_);
-      es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += 4.0 * static_cast<double>(n4) * 4.0;
+      const double algo = 4.0 * static_cast<double>(n4) * 4.0, touched = 4.0 * TILE_SLOTS * static_cast<double>(ctrl_->cand_tiles);
+      es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += algo; es_.scan_bytes_touched += touched;
+      if (ctrl_->cand_tiles * 10 >= static_cast<uint64_t>(n_tiles) * 9) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; }  // streams >= 90 % of the array
     }
+    cand_tiles_total_ += ctrl_->cand_tiles; tiles_total_ += n_tiles;
     *n = ctrl_->n_recs; *occurrences = ctrl_->occ;
     pt_n_ = ctrl_->pt_n;
     n_live_ -= ctrl_->occ;
@@ -918,6 +1125,7 @@ class CudaEngine : public Engine {
     cudaFreeAsync(len1, st_); cudaFreeAsync(sums, st_);
     cur_ = nxt; n_slots_ = S1; n_live_ = S1;
     es_.compactions++;
+    RC(build_planes());
     return 0;
   }
 
@@ -967,13 +1175,13 @@ class CudaEngine : public Engine {
     return 0;
   }
   uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) override {
-    if (!pt_.keys) return 0;
-    std::vector<uint64_t> k(pt_.cap), f(pt_.cap);
-    if (cudaMemcpy(k.data(), pt_.keys, pt_.cap * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    if (cudaMemcpy(f.data(), pt_.freq, pt_.cap * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (!pt_.ent) return 0;
+    cudaStreamSynchronize(st_);
+    std::vector<PairEnt> e(pt_.cap);
+    if (cudaMemcpy(e.data(), pt_.ent, pt_.cap * sizeof(PairEnt), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     uint64_t n = 0;
-    for (uint64_t s = 0; s < pt_.cap; s++) if (k[s] != PT_EMPTY) {
-      if (n < cap) { ab[2 * n] = static_cast<int32_t>(k[s] >> 32); ab[2 * n + 1] = static_cast<int32_t>(k[s] & 0xFFFFFFFFu); freq[n] = f[s]; }
+    for (uint64_t s = 0; s < pt_.cap; s++) if (e[s].key != PT_EMPTY) {
+      if (n < cap) { ab[2 * n] = static_cast<int32_t>(e[s].key >> 32); ab[2 * n + 1] = static_cast<int32_t>(e[s].key & 0xFFFFFFFFu); freq[n] = e[s].freq; }
       n++;
     }
     return n;
@@ -989,6 +1197,7 @@ class CudaEngine : public Engine {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
     out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_; out->merge_ms = merge_ms_;
+    out->cand_tiles = cand_tiles_total_; out->tiles_total = tiles_total_;
   }
   const char* name() override { return name_; }
 
@@ -1030,13 +1239,14 @@ class CudaEngine : public Engine {
     if (wl_) cudaFreeAsync(wl_, st_); wl_ = nullptr;
     for (int i = 0; i < 2; i++) { if (wid_[i]) cudaFreeAsync(wid_[i], st_); wid_[i] = nullptr; }
     if (claimed_) cudaFreeAsync(claimed_, st_); claimed_ = nullptr;
+    if (planes_) cudaFreeAsync(planes_, st_); planes_ = nullptr; plane_words_ = 0; id_cap_ = 0;
     n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
   }
   void release_all() {
     cudaSetDevice(dev_);
     release_corpus();
-    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); }
-    if (pt_.keys) { cudaFreeAsync(pt_.keys, st_); cudaFreeAsync(pt_.freq, st_); }
+    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); }
+    if (pt_.ent) cudaFreeAsync(pt_.ent, st_);
     if (recs_) cudaFreeHost(recs_);
     if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
     if (ctr_) cudaFreeAsync(ctr_, st_);
@@ -1065,7 +1275,10 @@ class CudaEngine : public Engine {
   uint32_t* wl_ = nullptr;
   uint32_t* wid_[2] = {nullptr, nullptr};
   uint32_t* claimed_ = nullptr;
-  uint32_t merge_no_ = 0;
+  uint32_t merge_no_ = 0, bar_count_ = 0;
+  uint32_t* planes_ = nullptr;
+  uint32_t plane_words_ = 0, id_cap_ = 0;
+  uint64_t cand_tiles_total_ = 0, tiles_total_ = 0;
   DeltaTable dt_{};
   PairTable pt_{};
   uint64_t pt_n_ = 0;
@@ -1079,6 +1292,9 @@ class CudaEngine : public Engine {
   uint64_t launches_ = 0, merge_seq_ = 0;
   double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0;
   int timing_every_ = 0;
+  ull* dbg_ = nullptr;
+  double dbg_acc_[5] = {0, 0, 0, 0, 0};
+  uint64_t dbg_n_ = 0;
   int scan_ctas_per_sm_ = 4;
 };
 

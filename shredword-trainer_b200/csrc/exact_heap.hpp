@@ -52,6 +52,10 @@ class ExactHeap {
     BPEHeapEntry x = d_[--n_];
     size_t i = 0;
     for (;;) {
+      // the walk is a chain of dependent cache misses once it leaves the hot top levels: pull in the eight
+      // great-grandchildren (contiguous, 192 bytes) while the next two levels are being compared
+      const size_t g = 8 * i + 7;
+      if (g < n_) { __builtin_prefetch(d_ + g); __builtin_prefetch(d_ + g + 3); __builtin_prefetch(d_ + g + 6); __builtin_prefetch(d_ + g + 7); }
       size_t l = 2 * i + 1, r = l + 1, best = i;
       uint64_t bf = x.freq;
       if (l < n_ && d_[l].freq > bf) { best = l; bf = d_[l].freq; }

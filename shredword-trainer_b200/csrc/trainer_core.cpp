@@ -180,15 +180,16 @@ void TrainerCore::init() {  // bpe.cpp:98-108
 void TrainerCore::apply_records(const Rec* recs, size_t n) {
   // FreqChangeMap iteration (bpe.cpp:297-298): bucket = key % 1024 ascending; inside a bucket the chain is LIFO by
   // first insertion (prepend at bpe.cpp:36-37)  ->  sort by (key & 1023, seq descending).
-  order_.assign(recs, recs + n);
-  std::sort(order_.begin(), order_.end(), [](const Rec& x, const Rec& y) {
-    uint32_t bx = static_cast<uint32_t>(x.key & 1023u), by = static_cast<uint32_t>(y.key & 1023u);
-    if (bx != by) return bx < by;
-    return x.seq > y.seq;
-  });
+  // one 64-bit sort key per record: bucket in the top bits, inverted sequence below (sequences are < 2^52)
+  sort_keys_.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    version_.prefetch(recs[i].key);
+    sort_keys_[i] = std::make_pair(((recs[i].key & 1023ull) << 52) | ((~recs[i].seq) & ((1ull << 52) - 1)), static_cast<uint32_t>(i));
+  }
+  std::sort(sort_keys_.begin(), sort_keys_.end());
   const uint64_t min_freq = abi_->config.min_pair_freq;
-  for (const Rec& r : order_) version_.prefetch(r.key);
-  for (const Rec& r : order_) {
+  for (const auto& sk : sort_keys_) {
+    const Rec& r = recs[sk.second];
     PairKey pk = unpack_key(r.key);
     switch (r.kind) {
       case REC_PUSH: {  // bpe.cpp:308-311
@@ -334,6 +335,8 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->heap_size = heap_.size(); s->heap_pushes = heap_.pushes; s->heap_pops = heap_.pops;
   s->merges = merges_last_; s->occurrences = occurrences_;
   s->scan_launches = es.scan_launches; s->scan_device_ms = es.scan_device_ms; s->scan_bytes = es.scan_bytes;
+  s->scan_bytes_touched = es.scan_bytes_touched; s->dense_launches = es.dense_launches; s->dense_device_ms = es.dense_device_ms; s->dense_bytes = es.dense_bytes;
+  s->cand_tiles = es.cand_tiles; s->tiles_total = es.tiles_total;
   s->count_launches = es.count_launches; s->count_device_ms = es.count_device_ms; s->count_bytes = es.count_bytes;
   s->ingest_launches = es.ingest_launches; s->ingest_device_ms = es.ingest_device_ms; s->ingest_bytes = es.ingest_bytes;
   s->kernel_launches = es.kernel_launches;

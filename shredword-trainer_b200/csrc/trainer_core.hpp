@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/shred_abi.h"
@@ -41,6 +42,7 @@ class TrainerCore {
   FlatMap<uint32_t> version_;   // pair key -> current version (absent = 0)
   FlatMap<uint64_t> phantom_;   // pair keys containing unk_id -> freq as the reference's table would hold it
   std::vector<Rec> order_;      // scratch: records in application order
+  std::vector<std::pair<uint64_t, uint32_t>> sort_keys_;
   LoadInfo info_;
   bool loaded_ = false;
   size_t merge_cap_ = 0;
