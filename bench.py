@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SHRED_BENCH_WORKLOAD", "config1_1GB"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas per GPU instead of one sharded job")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -151,7 +152,9 @@ def main():
     config = {"workload": f"{args.workload}: synthetic {mode} corpus {nbytes} bytes (gen_corpus seed={seed} w={w}), vocab_size={vocab} unk_id={unk} "
                           f"character_coverage={cov} min_pair_freq={mf}",
               "l2": "inputs_exceed_l2" if nbytes > 300_000_000 else "inputs_fit_l2_small_workload",
-              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU, no data-path collective)"}
+              "parallelism": "single GPU" if world == 1 else (f"{world} independent replicas (one per GPU, no data-path collective)" if args.replicas else
+                              f"one job, unique-word table sharded over {world} GPUs (contiguous word ranges); per-merge delta exchange inside the merge kernel "
+                              f"over NVLink peer memory (CUDA IPC); heap and pair table replicated")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -175,6 +178,12 @@ def main():
     os.environ["SHRED_QUIET"] = "1"
     os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "8")  # CUDA events around every 8th merge scan
     os.environ["SHRED_DEVICE"] = str(local_rank)
+    sharded = world > 1 and not args.replicas
+    if sharded:
+        import tempfile
+        box = [tempfile.mkdtemp(prefix="shred_rdv_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        os.environ.update(SHRED_RANK=str(rank), SHRED_WORLD=str(world), SHRED_RDV=box[0])
     import __graft_entry__ as ge
     if rank == 0:
         ge._load_build().build()
@@ -236,7 +245,7 @@ def main():
         tt = torch.tensor([train_dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         train_dev_ms, e2e_s, wall = tt.tolist()
-    total_merges = merges * args.steps * world
+    total_merges = merges * args.steps * (1 if sharded or world == 1 else world)
     st = steps[-1][3]
     all_ms = sum(s[3]["scan_device_ms"] for s in steps)
     all_bytes = sum(s[3]["scan_bytes"] for s in steps)
@@ -254,7 +263,7 @@ def main():
     achieved = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     line = {
         "metric": "bpe_train_merges_per_s", "value": total_merges / (train_dev_ms * 1e-3), "unit": "merges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": total_merges / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]) + 8 * merges,
                 "load_s_per_step": sum(s[1] for s in steps) / args.steps, "train_s_per_step": sum(s[2] for s in steps) / args.steps},
@@ -279,6 +288,16 @@ def main():
                    "h2d_ms": st["h2d_ms"], "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
     }
+    try:
+        big = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"].get(args.workload)
+        if big:
+            line["detail"]["golden_merges_md5"] = big["merges_md5"]
+            line["detail"]["bit_exact_vs_golden"] = big["merges_md5"] == line["detail"]["merges_md5"] and big["merges"] == merges
+    except Exception:
+        pass
+    if sharded and rank == 0:
+        import shutil
+        shutil.rmtree(os.environ["SHRED_RDV"], ignore_errors=True)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

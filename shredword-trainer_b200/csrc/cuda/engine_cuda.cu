@@ -31,8 +31,14 @@
 #include <vector>
 
 #include "../../../include/shred_abi.h"
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+
 #include "../charset.hpp"
 #include "../engine.hpp"
+#include "../shard.hpp"
 
 namespace shred {
 namespace {
@@ -61,7 +67,8 @@ constexpr uint64_t PT_EMPTY = ~0ull;
 constexpr uint64_t SEQ_MAX = ~0ull;
 constexpr int N_SM_FALLBACK = 148;
 
-enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32, ERR_BARRIER = 64 };
+enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32, ERR_BARRIER = 64,
+                  ERR_PEER_TIMEOUT = 128, ERR_INBOX_FULL = 256 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -74,7 +81,7 @@ __device__ __forceinline__ uint64_t fc_key(int32_t a, int32_t b) {  // bpe.cpp:2
 
 struct Ctrl {  // mapped pinned host memory, written by finalize_block
   volatile uint64_t flag;
-  uint64_t n_recs, occ, pt_n, n_leaders, n_keys, cand_tiles;
+  uint64_t n_recs, occ, occ_local, pt_n, n_leaders, n_keys, cand_tiles;
   uint32_t err, pad;
 };
 
@@ -374,7 +381,7 @@ __device__ __forceinline__ int32_t code_to_id(int32_t code, const Params& P) { r
 
 // bpe.cpp:197-214: every adjacent pair without unk adds the word's count; first sighting = flat position
 __global__ void __launch_bounds__(256) k_count(const int32_t* __restrict__ ids, const ull* __restrict__ woff, const uint32_t* __restrict__ wlen,
-                                               const ull* __restrict__ wcnt, uint32_t n_words, Params P, DeltaTable dt, DevCounters* ctr) {
+                                               const ull* __restrict__ wcnt, uint32_t n_words, Params P, DeltaTable dt, DevCounters* ctr, uint64_t seq_base) {
   for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += gridDim.x * blockDim.x) {
     const ull base = woff[wi] + 1;
     const uint32_t len = wlen[wi];
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(256) k_count(const int32_t* __restrict__ ids, 
     int32_t a = ids[base];
     for (uint32_t j = 0; j + 1 < len; j++) {
       const int32_t b = ids[base + j + 1];
-      if (a != P.unk_code && b != P.unk_code) dt_add(dt, ctr, fc_key(a, b), c, base + j);
+      if (a != P.unk_code && b != P.unk_code) dt_add(dt, ctr, fc_key(a, b), c, seq_base | (base + j));
       a = b;
     }
   }
@@ -480,6 +487,7 @@ __device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairT
   if (threadIdx.x == 0) {  // counters for the host, then re-arm them for the next pass
     ctrl->n_recs = s_rec_n < rec_cap ? s_rec_n : rec_cap;
     ctrl->occ = ctr->occ;
+    ctrl->occ_local = ctr->occ;
     ctrl->pt_n = ctr->pt_n;
     ctrl->n_leaders = ctr->wl_n;
     ctrl->n_keys = ctr->dt_n;
@@ -503,7 +511,7 @@ __global__ void __launch_bounds__(256) k_finalize_count(DeltaTable dt, PairTable
 // symbols before p were themselves merged in this pass), right neighbour = the raw id two slots on.
 __device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
                                                 int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
-                                                uint32_t& my_occ) {
+                                                uint32_t& my_occ, uint64_t seq_base) {
   const int32_t l1 = ids[p - 1];
   const uint32_t wi = wid[p];  // independent loads first: wid -> wcnt is the longest chain
   const int32_t r2 = ids[p + 2];
@@ -517,7 +525,7 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, 
     left_merged = p > q;
   }
   const int64_t c = static_cast<int64_t>(wcnt[wi]);
-  const uint64_t seq = p * 4ull;
+  const uint64_t seq = seq_base | (p * 4ull);
   if (l1 >= 0) {
     const int32_t lid = left_merged ? N : code_to_id(l1, P);
     dt_add(dt, ctr, fc_key(lid, A), -c, seq + 0);
@@ -530,6 +538,24 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, 
   }
   ml[atomicAdd(&ctr->wl_n, 1u)] = static_cast<uint32_t>(p);
   ++my_occ;
+}
+
+// ---- multi-GPU exchange over NVLink peer memory ---------------------------------------------------------------
+// Every rank owns a contiguous range of the unique words and a full replica of the pair table and of the host heap.
+// Per pass (count, merge, token frequencies) each rank's aggregated (key, delta, sequence) list is the only thing that
+// crosses GPUs: the kernel STORES it straight into every peer's inbox (memory mapped with CUDA IPC, NVLink/NVSwitch),
+// raises a sequence flag there, waits for the peers' flags in its own inbox, and folds their entries into its own delta
+// table.  No host round trip and no NCCL call sits between the scan and the pair-table update.
+constexpr int MAX_RANKS = 8;
+constexpr uint64_t INBOX_ENTRIES = 1ull << 20, INBOX_HDR = 64, INBOX_BYTES = INBOX_HDR + INBOX_ENTRIES * 24;
+struct InboxHdr { ull seq; ull n; ull aux; };
+struct DistArgs {
+  int rank, world;
+  uint8_t* peer[MAX_RANKS];  // inbox base of every rank (peer[rank] is local memory)
+  ull xseq;                  // exchange number (>= 1); its parity selects the inbox half
+};
+__device__ __forceinline__ uint8_t* inbox_region(uint8_t* base, int world, ull xseq, int src) {
+  return base + ((xseq & 1ull) * static_cast<ull>(world) + static_cast<ull>(src)) * INBOX_BYTES;
 }
 
 // Software grid barrier for the cooperative per-merge kernel (all CTAs are co-resident: cudaLaunchCooperativeKernel).
@@ -548,6 +574,91 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uin
   __syncthreads();
 }
 
+// Cooperative exchange of the delta table's dense list (klist/list/delta/seq) between ranks: 3 grid barriers.
+// On return the local delta table holds the GLOBAL aggregate and *occ_global the global occurrence count.
+__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, uint32_t bar_base, int first_barrier, ull occ_local,
+                                                ull* occ_global) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t n_local = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
+  if (n_local > INBOX_ENTRIES && gtid == 0) atomicOr(&ctr->err, ERR_INBOX_FULL);
+  const uint32_t n_send = n_local < INBOX_ENTRIES ? n_local : static_cast<uint32_t>(INBOX_ENTRIES);
+  for (uint32_t i = gtid; i < n_send; i += gthreads) {  // P2P stores into every peer's inbox
+    const uint32_t ds = dt.list[i];
+    const ull k = dt.klist[i], d = dt.delta[ds], sq = dt.seq[ds];
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
+      ull* e = reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR) + 3ull * i;
+      e[0] = k; e[1] = d; e[2] = sq;
+    }
+  }
+  __threadfence_system();
+  grid_barrier(&ctr->bar, bar_base + (first_barrier + 0) * gridDim.x, &ctr->err);
+  if (gtid == 0) {
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
+      InboxHdr* h = reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank));
+      h->n = n_send; h->aux = occ_local;
+    }
+    __threadfence_system();
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
+      *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
+    const long long t0 = clock64();
+    for (int src = 0; src < D.world; src++) if (src != D.rank) {  // wait for every peer's list to land in MY inbox
+      volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
+      while (*f != D.xseq) if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }  // ~4 s: never hang the GPU
+    }
+    __threadfence_system();
+  }
+  grid_barrier(&ctr->bar, bar_base + (first_barrier + 1) * gridDim.x, &ctr->err);
+  ull occ = occ_local;
+  for (int src = 0; src < D.world; src++) if (src != D.rank) {  // fold the peers' entries into my delta table
+    const uint8_t* reg = inbox_region(D.peer[D.rank], D.world, D.xseq, src);
+    const InboxHdr* h = reinterpret_cast<const InboxHdr*>(reg);
+    const ull n_src = __ldcv(&h->n);
+    occ += __ldcv(&h->aux);
+    const ull* e = reinterpret_cast<const ull*>(reg + INBOX_HDR);
+    for (ull i = gtid; i < n_src && i < INBOX_ENTRIES; i += gthreads)
+      dt_add(dt, ctr, __ldcv(e + 3 * i), static_cast<int64_t>(__ldcv(e + 3 * i + 1)), __ldcv(e + 3 * i + 2));
+  }
+  *occ_global = occ;
+  grid_barrier(&ctr->bar, bar_base + (first_barrier + 2) * gridDim.x, &ctr->err);
+}
+
+// count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
+__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
+                                                             uint64_t flag_value, DistArgs D, uint32_t bar_base) {
+  ull occ;
+  exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);
+  if (blockIdx.x == 0) finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
+}
+
+// token frequencies, sharded: sum of the ranks' partial arrays (T x uint64), same inbox protocol
+__global__ void __launch_bounds__(256) k_dist_sum_u64(ull* vals, uint64_t T, DevCounters* ctr, DistArgs D, uint32_t bar_base) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  for (uint64_t i = gtid; i < T; i += gthreads) {
+    const ull v = vals[i];
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
+      reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR)[i] = v;
+  }
+  __threadfence_system();
+  grid_barrier(&ctr->bar, bar_base + 1 * gridDim.x, &ctr->err);
+  if (gtid == 0) {
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
+      *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
+    const long long t0 = clock64();
+    for (int src = 0; src < D.world; src++) if (src != D.rank) {
+      volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
+      while (*f != D.xseq) if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }
+    }
+    __threadfence_system();
+  }
+  grid_barrier(&ctr->bar, bar_base + 2 * gridDim.x, &ctr->err);
+  for (uint64_t i = gtid; i < T; i += gthreads) {
+    ull v = vals[i];
+    for (int src = 0; src < D.world; src++) if (src != D.rank)
+      v += __ldcv(reinterpret_cast<const ull*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src) + INBOX_HDR) + i);
+    vals[i] = v;
+  }
+}
+
 // The per-merge kernel (cooperative launch, persistent grid = SM count x resident CTAs).
 //   phase 1  HBM-bound scan of the candidate tiles: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs
 //            that start in it; an occurrence emits its count deltas straight into the delta table and is remembered
@@ -556,13 +667,13 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uin
 //            the last CTA to finish publishes the counters and the flag the host spins on
 //   phase 3  in-place left-packed rewrite of the touched words (bpe.cpp:291-296), off the host's critical path: the
 //            first occurrence to claim a word (claimed[wi] = merge number) rewrites it; the last CTA re-arms the counters
-template <int UNROLL>
+template <int UNROLL, bool DIST>
 __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint32_t n_tiles, uint32_t tiles_per_cta,
                                                const uint32_t* __restrict__ planeA, const uint32_t* __restrict__ planeB, uint32_t* planes, uint32_t W, uint32_t id_cap,
                                                const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, const ull* __restrict__ woff, uint32_t* wlen,
                                                uint32_t* claimed, uint32_t merge_no, int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt,
                                                DevCounters* ctr, uint32_t* __restrict__ ml, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, uint64_t flag_value,
-                                               uint32_t bar_target, ull* dbg) {
+                                               uint32_t bar_base, ull* dbg, DistArgs D) {
   __shared__ uint32_t cand[MAX_TILES_PER_CTA];
   __shared__ uint32_t n_cand;
   __shared__ bool last;
@@ -612,7 +723,7 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
           while (m) {
             const int k = __ffs(m) - 1;
             m &= m - 1;
-            emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ);
+            emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull);
           }
         }
       }
@@ -622,8 +733,11 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
   for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
   if (lane == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
   if (threadIdx.x == 0 && nc_total) atomicAdd(&ctr->cand_tiles, nc_total);
-  grid_barrier(&ctr->bar, bar_target, &ctr->err);
+  grid_barrier(&ctr->bar, bar_base + gridDim.x, &ctr->err);
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[1] = gtime();
+  const ull occ_local = ctr->occ;
+  ull occ_global = occ_local;
+  if (DIST) exchange_deltas(dt, ctr, D, bar_base, 2, occ_local, &occ_global);
 
   // ---- phase 2: fold the aggregated deltas into the pair table, one key per thread
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -672,7 +786,8 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
     __threadfence();
     const uint32_t nr = *reinterpret_cast<volatile uint32_t*>(&ctr->rec_n);
     ctrl->n_recs = nr < rec_cap ? nr : rec_cap;
-    ctrl->occ = *reinterpret_cast<volatile ull*>(&ctr->occ);
+    ctrl->occ = occ_global;
+    ctrl->occ_local = occ_local;
     ctrl->pt_n = *reinterpret_cast<volatile ull*>(&ctr->pt_n);
     ctrl->n_leaders = *reinterpret_cast<volatile uint32_t*>(&ctr->wl_n);
     ctrl->n_keys = n_keys;
@@ -734,6 +849,9 @@ __global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {
 
 // ------------------------------------------------------------------------------------------------ compaction / save
 
+__global__ void k_rebase(const ull* in, uint32_t n, ull base, ull* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i] - base;
+}
 __global__ void k_len1(const uint32_t* wlen, uint32_t n, ull* len1) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) len1[i] = static_cast<ull>(wlen[i]) + 1ull;
 }
@@ -790,11 +908,88 @@ class CudaEngine : public Engine {
       dbg_ = static_cast<ull*>(dp);
     }
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4, false>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
+    if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
+    if (world_ > 1) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4, true>, 256, 0) == cudaSuccess && nb > 0 && nb < scan_ctas_per_sm_) scan_ctas_per_sm_ = nb;
+      const char* r = std::getenv("SHRED_RANK");
+      rank_ = r ? std::atoi(r) : 0;
+      if (world_ > MAX_RANKS || rank_ < 0 || rank_ >= world_) { std::fprintf(stderr, "[ERROR]\t bad SHRED_RANK/SHRED_WORLD (%d/%d, at most %d ranks)\n", rank_, world_, MAX_RANKS); return -1; }
+      RC(dist_setup());
+    } else { world_ = 1; rank_ = 0; }
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     return 0;
   }
+
+  // ------------------------------------------------------------------------------------------------- multi-GPU setup
+  // One process per GPU.  Every rank allocates its inbox with cudaMalloc, exports it with CUDA IPC through a small file
+  // in the rendezvous directory SHRED_RDV (shared by the ranks of one job) and maps every peer's inbox.
+  int dist_setup() {
+    static int instance = 0;  // ranks create their trainers in the same order, so instance numbers agree
+    const int inst = instance++;
+    const char* rdv = std::getenv("SHRED_RDV");
+    if (!rdv || !*rdv) { std::fprintf(stderr, "[ERROR]\t SHRED_WORLD > 1 needs SHRED_RDV (a directory shared by the ranks)\n"); return -1; }
+    const size_t bytes = 2ull * world_ * INBOX_BYTES;
+    CK(cudaMalloc(reinterpret_cast<void**>(&inbox_), bytes));
+    CK(cudaMemset(inbox_, 0, bytes));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, inbox_));
+    auto path = [&](int r, const char* ext) { return std::string(rdv) + "/inst" + std::to_string(inst) + "_rank" + std::to_string(r) + ext; };
+    {
+      const std::string tmp = path(rank_, ".tmp"), fin = path(rank_, ".ipc");
+      FILE* f = std::fopen(tmp.c_str(), "wb");
+      if (!f) { std::fprintf(stderr, "[ERROR]\t cannot write %s\n", tmp.c_str()); return -1; }
+      std::fwrite(&mine, sizeof mine, 1, f);
+      std::fclose(f);
+      if (std::rename(tmp.c_str(), fin.c_str()) != 0) return -1;
+    }
+    for (int r = 0; r < MAX_RANKS; r++) dist_.peer[r] = nullptr;
+    dist_.rank = rank_; dist_.world = world_; dist_.xseq = 0;
+    dist_.peer[rank_] = inbox_;
+    const double t0 = now_ms();
+    for (int r = 0; r < world_; r++) if (r != rank_) {
+      cudaIpcMemHandle_t h;
+      for (;;) {
+        FILE* f = std::fopen(path(r, ".ipc").c_str(), "rb");
+        if (f) { size_t got = std::fread(&h, sizeof h, 1, f); std::fclose(f); if (got == 1) break; }
+        if (now_ms() - t0 > 120000.0) { std::fprintf(stderr, "[ERROR]\t rank %d: timed out waiting for rank %d in %s\n", rank_, r, rdv); return -1; }
+        usleep(1000);
+      }
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      dist_.peer[r] = static_cast<uint8_t*>(p);
+    }
+    // nobody may unlink its file before every rank has opened every handle
+    { FILE* f = std::fopen(path(rank_, ".ok").c_str(), "wb"); if (f) std::fclose(f); }
+    for (int r = 0; r < world_; r++) {
+      struct stat st;
+      while (stat(path(r, ".ok").c_str(), &st) != 0) {
+        if (now_ms() - t0 > 120000.0) { std::fprintf(stderr, "[ERROR]\t rank %d: rank %d never finished its setup\n", rank_, r); return -1; }
+        usleep(1000);
+      }
+    }
+    rdv_prefix_ = std::string(rdv) + "/inst" + std::to_string(inst) + "_rank";
+    return 0;
+  }
+  void dist_teardown() {
+    if (world_ <= 1 || !inbox_) return;
+    for (int r = 0; r < world_; r++) if (r != rank_ && dist_.peer[r]) cudaIpcCloseMemHandle(dist_.peer[r]);
+    // exported memory must outlive every peer's mapping: free only after all ranks have closed their handles
+    if (!rdv_prefix_.empty()) {
+      { FILE* f = std::fopen((rdv_prefix_ + std::to_string(rank_) + ".closed").c_str(), "wb"); if (f) std::fclose(f); }
+      const double t0 = now_ms();
+      for (int r = 0; r < world_; r++) {
+        struct stat st;
+        while (stat((rdv_prefix_ + std::to_string(r) + ".closed").c_str(), &st) != 0 && now_ms() - t0 < 20000.0) usleep(500);
+      }
+    }
+    cudaFree(inbox_);
+    inbox_ = nullptr;
+    // the small rendezvous files stay: the job that created the directory removes it
+  }
+  DistArgs next_exchange() { DistArgs d = dist_; d.xseq = ++dist_.xseq; return d; }
 
   // ---------------------------------------------------------------------------------------------------------- load
   int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) override {
@@ -908,6 +1103,34 @@ class CudaEngine : public Engine {
     es_.d2h_bytes += 256 * 8 + 8 + sizeof(DevCounters);
     charset_keep(info->hist, cfg_.coverage, info->keep, &info->n_distinct, &info->n_keep);
     info->n_symbols = S1 - N;
+    uint32_t lo = 0, n_local = N;
+    host_counts_.clear();
+    if (world_ > 1 && N) {  // keep only this rank's contiguous range of words (shard.hpp); ingest itself is replicated
+      std::vector<ull> hoff(static_cast<size_t>(N) + 1);
+      CK(cudaMemcpyAsync(hoff.data(), woff_[0], static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost, st_));
+      host_counts_.resize(N);
+      CK(cudaMemcpyAsync(host_counts_.data(), wcnt_, static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost, st_));
+      CK(cudaStreamSynchronize(st_));
+      hoff[N] = S1;
+      lo = static_cast<uint32_t>(shard_begin(hoff.data(), N, rank_, world_));
+      const uint32_t hi = static_cast<uint32_t>(shard_begin(hoff.data(), N, rank_ + 1, world_));
+      n_local = hi - lo;
+      const ull base_off = hoff[lo];
+      S1 = hoff[hi] - base_off;
+      ull *wc = nullptr, *wo0 = nullptr, *wo1 = nullptr; uint32_t* wl = nullptr;
+      const uint64_t nl = n_local ? n_local : 1;
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wc), nl * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wl), nl * 4, st_));
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wo0), (nl + 1) * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wo1), (nl + 1) * 8, st_));
+      if (n_local) {
+        CK(cudaMemcpyAsync(wc, wcnt_ + lo, static_cast<uint64_t>(n_local) * 8, cudaMemcpyDeviceToDevice, st_));
+        CK(cudaMemcpyAsync(wl, wlen_ + lo, static_cast<uint64_t>(n_local) * 4, cudaMemcpyDeviceToDevice, st_));
+        k_rebase<<<grid_for(n_local, 256), 256, 0, st_>>>(woff_[0] + lo, n_local, base_off, wo0); launches_++;
+      }
+      cudaFreeAsync(wcnt_, st_); cudaFreeAsync(wlen_, st_); cudaFreeAsync(woff_[0], st_); cudaFreeAsync(woff_[1], st_);
+      wcnt_ = wc; wlen_ = wl; woff_[0] = wo0; woff_[1] = wo1;
+      es_.d2h_bytes += static_cast<uint64_t>(N) * 16;
+    }
+    n_words_ = n_local;
     n_slots_ = S1; n_live_ = S1;
     if (S1 + 64 >= (1ull << 32)) { free_tmp(); free_wt(); std::fprintf(stderr, "[ERROR]\t corpus needs more than 2^32 symbol slots on one GPU\n"); return -1; }
     ids_cap_ = ((S1 + 8 + 1023) / 1024) * 1024;
@@ -920,8 +1143,8 @@ class CudaEngine : public Engine {
     merge_no_ = 0;
     cur_ = 0;
     CK(cudaMemcpyAsync(d_keep, info->keep, 256, cudaMemcpyHostToDevice, st_));
-    CK(cudaMemcpyAsync(woff_[0] + N, &S1, 8, cudaMemcpyHostToDevice, st_));
-    if (N) { k_symbolize<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, woff_[0], d_keep, P_.unk_code, ids_[0], wid_[0]); launches_++; es_.ingest_launches++; }
+    CK(cudaMemcpyAsync(woff_[0] + n_local, &S1, 8, cudaMemcpyHostToDevice, st_));
+    if (n_local) { k_symbolize<<<grid_for(n_local, 256), 256, 0, st_>>>(d_text, wt, order_slot + lo, n_local, woff_[0], d_keep, P_.unk_code, ids_[0], wid_[0]); launches_++; es_.ingest_launches++; }
     k_fill_i32<<<grid_for(ids_cap_ - S1, 256), 256, 0, st_>>>(ids_[0], S1, ids_cap_, DEAD); launches_++; es_.ingest_launches++;
     CK(cudaStreamSynchronize(st_));
     CK(cudaGetLastError());
@@ -1009,7 +1232,7 @@ class CudaEngine : public Engine {
       pt_n_ = 0;
       ++flag_;
       CK(cudaEventRecord(ev0_, st_));
-      if (n_words_) { k_count<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, dt_, ctr_); launches_++; }
+      if (n_words_) { k_count<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, dt_, ctr_, world_ > 1 ? seq_base(rank_) : 0ull); launches_++; }
       CK(cudaEventRecord(ev1_, st_));
       // the finalize pass needs dt_n <= cap/2 and room in the pair table: check before consuming the delta table
       DevCounters c;
@@ -1021,8 +1244,20 @@ class CudaEngine : public Engine {
         RC(alloc_dt(static_cast<uint64_t>(dt_.cap) * 4));
         continue;
       }
-      RC(grow_pt(static_cast<uint64_t>(c.dt_n) + 4ull * (256 + vocab_hint_) + 1024));
-      k_finalize_count<<<1, 256, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), P_, flag_); launches_++;
+      RC(grow_pt((world_ > 1 ? static_cast<uint64_t>(dt_.cap) / 2 : static_cast<uint64_t>(c.dt_n)) + 4ull * (256 + vocab_hint_) + 1024));  // replicas must size identically
+      if (world_ > 1) {
+        DistArgs a_D = next_exchange();
+        const int grid = n_sm_ * 2;
+        uint32_t a_reccap = rec_cap_, a_bar = bar_count_;
+        Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
+        uint64_t a_flag = flag_;
+        bar_count_ += 3u * static_cast<uint32_t>(grid);
+        void* args[] = {&dt_, &pt_, &ctr_, &recs_, &a_reccap, &a_ctrl, &P_, &a_flag, &a_D, &a_bar};
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_count_finalize), dim3(grid), dim3(256), args, 0, st_));
+      } else {
+        k_finalize_count<<<1, 256, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), P_, flag_);
+      }
+      launches_++;
       RC(wait_flag());
       if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", ctrl_->err); return -1; }
       es_.count_launches++; es_.count_device_ms += ms; es_.count_bytes += 4.0 * static_cast<double>(n_live_) + 12.0 * n_words_;
@@ -1065,11 +1300,14 @@ class CudaEngine : public Engine {
       int32_t a_A = a, a_B = b, a_N = new_id;
       Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
       uint64_t a_flag = flag_;
-      bar_count_ += static_cast<uint32_t>(grid);  // one grid barrier per launch; the counter only grows (wraps mod 2^32)
-      uint32_t a_bar = bar_count_;
+      uint32_t a_bar = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
+      DistArgs a_D = dist_;
+      if (world_ > 1) a_D = next_exchange();
+      bar_count_ += (world_ > 1 ? 4u : 1u) * static_cast<uint32_t>(grid);
       void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
-                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &dbg_};
-      CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_merge<4>), dim3(grid), dim3(256), args, 0, st_));
+                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &dbg_, &a_D};
+      CK(cudaLaunchCooperativeKernel(world_ > 1 ? reinterpret_cast<void*>(k_merge<4, true>) : reinterpret_cast<void*>(k_merge<4, false>), dim3(grid), dim3(256), args,
+                                     0, st_));
     }
     if (timed) CK(cudaEventRecord(ev1_, st_));
     launches_ += 1;
@@ -1095,7 +1333,7 @@ class CudaEngine : public Engine {
     cand_tiles_total_ += ctrl_->cand_tiles; tiles_total_ += n_tiles;
     *n = ctrl_->n_recs; *occurrences = ctrl_->occ;
     pt_n_ = ctrl_->pt_n;
-    n_live_ -= ctrl_->occ;
+    n_live_ -= ctrl_->occ_local;
     es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
     merge_ms_ += now_ms() - tm0;
     return 0;
@@ -1132,11 +1370,22 @@ class CudaEngine : public Engine {
   // ---------------------------------------------------------------------------------------------------------- save
   int token_freqs(uint64_t* freq, size_t T) override {
     CK(cudaSetDevice(dev_));
-    if (!loaded_ || !n_words_ || !T) return 0;
+    if (!loaded_ || (!n_words_ && world_ == 1) || !T) return 0;
     ull* d = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&d), T * 8, st_));
     CK(cudaMemsetAsync(d, 0, T * 8, st_));
-    k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, d, T); launches_++;
+    if (n_words_) { k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, d, T); launches_++; }
+    if (world_ > 1) {
+      if (T > INBOX_ENTRIES * 3) { cudaFreeAsync(d, st_); std::fprintf(stderr, "[ERROR]\t vocabulary too large for the exchange buffer\n"); return -1; }
+      DistArgs a_D = next_exchange();
+      const int grid = n_sm_ * 2;
+      uint64_t a_T = T;
+      uint32_t a_bar = bar_count_;
+      bar_count_ += 2u * static_cast<uint32_t>(grid);
+      void* args[] = {&d, &a_T, &ctr_, &a_D, &a_bar};
+      CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_sum_u64), dim3(grid), dim3(256), args, 0, st_));
+      launches_++;
+    }
     CK(cudaMemcpyAsync(freq, d, T * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
     cudaFreeAsync(d, st_);
@@ -1144,6 +1393,7 @@ class CudaEngine : public Engine {
     return 0;
   }
   int word_counts(uint64_t* out) override {
+    if (world_ > 1) { std::memcpy(out, host_counts_.data(), host_counts_.size() * 8); return 0; }  // global counts, kept from ingest
     if (!n_words_) return 0;
     CK(cudaMemcpyAsync(out, wcnt_, static_cast<uint64_t>(n_words_) * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
@@ -1251,6 +1501,7 @@ class CudaEngine : public Engine {
     if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
     if (ctr_) cudaFreeAsync(ctr_, st_);
     if (st_) cudaStreamSynchronize(st_);
+    dist_teardown();
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (evm0_) cudaEventDestroy(evm0_);
@@ -1276,6 +1527,11 @@ class CudaEngine : public Engine {
   uint32_t* wid_[2] = {nullptr, nullptr};
   uint32_t* claimed_ = nullptr;
   uint32_t merge_no_ = 0, bar_count_ = 0;
+  int rank_ = 0, world_ = 1;
+  DistArgs dist_{};
+  uint8_t* inbox_ = nullptr;
+  std::vector<uint64_t> host_counts_;
+  std::string rdv_prefix_;
   uint32_t* planes_ = nullptr;
   uint32_t plane_words_ = 0, id_cap_ = 0;
   uint64_t cand_tiles_total_ = 0, tiles_total_ = 0;
