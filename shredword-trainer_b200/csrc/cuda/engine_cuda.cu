@@ -14,7 +14,7 @@
 // Kernels (reference loop each one replaces)
 //   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise on \t\r\n space, unique-word table insert
 //   k_hist ............ histogram.cpp:30-36                unweighted byte histogram over unique words
-//   k_scatter/k_rank .. hash.cpp:61-72                     word order = (djb2 & 4095, first occurrence)
+//   k_scatter/k_sort_buckets  hash.cpp:61-72               word order = (djb2 & 4095, first occurrence)
 //   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids with unk substitution
 //   k_count ........... bpe.cpp:187-218                    adjacent pair counts
 //   k_merge ........... bpe.cpp:265-318                    one cooperative launch per merge: HBM-bound scan of the candidate tiles
@@ -102,6 +102,7 @@ struct DeltaTable {
 struct PairEnt { uint64_t key; uint64_t freq; };  // one 16-byte load fetches both
 struct PairTable {
   PairEnt* ent;
+  uint32_t* serial;  // dense id per entry = number of entries that existed when it was created (the host indexes by it)
   uint64_t mask; uint64_t cap;
 };
 
@@ -142,7 +143,7 @@ __device__ __forceinline__ uint64_t pt_find_or_insert(const PairTable& pt, DevCo
     if (e.x == key) { *old_freq = e.y; return slot; }
     if (e.x == PT_EMPTY) {
       const uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
-      if (prev == PT_EMPTY) { atomicAdd(&ctr->pt_n, 1ull); *old_freq = 0; return slot; }
+      if (prev == PT_EMPTY) { pt.serial[slot] = static_cast<uint32_t>(atomicAdd(&ctr->pt_n, 1ull)); *old_freq = 0; return slot; }
       if (prev == key) { *old_freq = pt.ent[slot].freq; return slot; }
     }
     slot = (slot + 1) & pt.mask;
@@ -215,8 +216,14 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ te
           } else cur = prevt;
         }
         if (cur == tag) {
-          const ull old = atomicMin(&wt.first[slot], static_cast<ull>(off));
-          atomicAdd(&wt.count[slot], 1ull);
+          // first occurrence: most tokens come after the word's first sighting, so look before paying for an atomic
+          ull old = *reinterpret_cast<volatile ull*>(&wt.first[slot]);
+          if (off < old) old = atomicMin(&wt.first[slot], static_cast<ull>(off));
+          {  // count: lanes of this warp that hit the same slot right now add once (hot words are most of a Zipf corpus)
+            const unsigned am = __activemask();
+            const unsigned grp = __match_any_sync(am, slot);
+            if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(grp) - 1)) atomicAdd(&wt.count[slot], static_cast<ull>(__popc(grp)));
+          }
           if (old != SEQ_MAX && old != off) {  // same tag: must be the same bytes, else retry ingest with a new seed
             bool same = is_delim(text[old + len]);
             for (uint32_t j = 0; j < len && same; j++) same = text[old + j] == text[off + j];
@@ -267,11 +274,41 @@ __global__ void k_scatter(WordTable wt, const uint32_t* u_slot, uint32_t n, cons
   }
 }
 
-// rank of each word inside its bucket by first occurrence (all first offsets are distinct): wi = bucket_start + rank
-__global__ void k_rank(WordTable wt, const uint32_t* tmp_slot, const ull* tmp_first, uint32_t n, const uint32_t* bstart, uint32_t* order_slot) {
+// order of the words inside a djb2 bucket = first occurrence (all first offsets are distinct): wi = bucket_start + rank.
+// One CTA per bucket: bitonic sort of (first_offset << 24 | index) in shared memory.  Buckets larger than SORT_CAP
+// (more than ~30 M unique words) are left to k_rank_big.
+constexpr uint32_t SORT_CAP = 8192, SORT_THREADS = 512;
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_buckets(const uint32_t* __restrict__ tmp_slot, const ull* __restrict__ tmp_first, const uint32_t* __restrict__ bstart,
+                                                               uint32_t* __restrict__ order_slot) {
+  extern __shared__ ull sk[];
+  const uint32_t b = blockIdx.x, bs = bstart[b], n = bstart[b + 1] - bs;
+  if (n == 0 || n > SORT_CAP) return;
+  uint32_t np = 1;
+  while (np < n) np <<= 1;
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) sk[i] = i < n ? ((tmp_first[bs + i] << 24) | i) : ~0ull;
+  __syncthreads();
+  for (uint32_t k = 2; k <= np; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const ull a = sk[i], c = sk[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { sk[i] = c; sk[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order_slot[bs + i] = tmp_slot[bs + static_cast<uint32_t>(sk[i] & 0xFFFFFFull)];
+}
+
+// fallback for oversized buckets: each element counts the smaller first offsets in its bucket (O(n_b^2), L1 broadcast)
+__global__ void k_rank_big(WordTable wt, const uint32_t* tmp_slot, const ull* tmp_first, uint32_t n, const uint32_t* bstart, uint32_t* order_slot) {
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const uint32_t s = tmp_slot[e], b = wt.bucket[s];
     const uint32_t bs = bstart[b], be = bstart[b + 1];
+    if (be - bs <= SORT_CAP) continue;
     const ull mine = tmp_first[e];
     uint32_t rank = 0;
     for (uint32_t j = bs; j < be; j++) rank += tmp_first[j] < mine ? 1u : 0u;
@@ -399,11 +436,11 @@ __global__ void __launch_bounds__(256) k_count(const int32_t* __restrict__ ids, 
 // -------------------------------------------------------------------------------------------------------------- merge
 
 // ---- tile occurrence index ------------------------------------------------------------------------------------
-// planes[id * W + (t >> 5)] bit (t & 31) is set if token `id` occurs in slots [1024 t, 1024 t + 1024] (the first slot of
+// planes[id * W + (t >> 5)] bit (t & 31) is set if token `id` occurs in slots [512 t, 512 t + 512] (the first slot of
 // the next tile included, so a pair that straddles the boundary is found from tile t).  Bits are only ever added between
 // two compactions, so the index is a superset of the truth: a merge scans exactly the tiles whose bit is set for both A
 // and B and provably misses nothing.  Late merges touch a few hundred of tens of thousands of tiles.
-constexpr uint32_t TILE_SHIFT = 10, TILE_SLOTS = 1u << TILE_SHIFT, TILE_I4 = TILE_SLOTS / 4, MAX_TILES_PER_CTA = 1024;
+constexpr uint32_t TILE_SHIFT = 9, TILE_SLOTS = 1u << TILE_SHIFT, TILE_I4 = TILE_SLOTS / 4, MAX_TILES_PER_CTA = 1024;
 static_assert(TILE_I4 % (32 * 4) == 0, "a tile is a whole number of warp chunks");
 
 __device__ __forceinline__ void plane_set(uint32_t* planes, uint32_t W, uint32_t id_cap, int32_t id, uint64_t slot) {
@@ -462,7 +499,7 @@ __device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairT
     for (int j = 0; j < ILP; j++) if (ok[j]) {
       dt.keys[ds[j]] = dt.empty; dt.delta[ds[j]] = 0ull; dt.seq[ds[j]] = SEQ_MAX;  // re-arm the scratch slot
       const int32_t pa = static_cast<int32_t>(key[j] >> 32), pb = static_cast<int32_t>(key[j] & 0xFFFFFFFFu);  // bpe.cpp:301
-      Rec out; out.key = key[j]; out.seq = sq[j]; out.pad = 0; out.kind = REC_PUSH; out.val = 0;
+      Rec out; out.key = key[j]; out.seq = sq[j]; out.serial = REC_NO_SERIAL; out.kind = REC_PUSH; out.val = 0;
       bool emit = false;
       if (!COUNT && pa == A && pb == B) continue;  // bpe.cpp:302
       if (!COUNT && (pa == P.unk_id || pb == P.unk_id)) {  // phantom pair: tracked by the host (Appendix A12)
@@ -475,6 +512,7 @@ __device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairT
         pt.ent[s].freq = nf;
         if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
         else if (!COUNT && old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
+        if (emit) out.serial = pt.serial[s];
       }
       if (emit) {
         const uint32_t idx = atomicAdd(&s_rec_n, 1u);
@@ -758,7 +796,7 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
     dt.keys[ds] = dt.empty; dt.delta[ds] = 0ull; dt.seq[ds] = SEQ_MAX;  // re-arm the scratch slot
     const int32_t pa = static_cast<int32_t>(key >> 32), pb = static_cast<int32_t>(key & 0xFFFFFFFFu);  // bpe.cpp:301
     if (pa == A && pb == B) continue;  // bpe.cpp:302
-    Rec out; out.key = key; out.seq = sq; out.pad = 0; out.kind = REC_PUSH; out.val = 0;
+    Rec out; out.key = key; out.seq = sq; out.serial = REC_NO_SERIAL; out.kind = REC_PUSH; out.val = 0;
     bool emit = false;
     if (pa == P.unk_id || pb == P.unk_id) {  // phantom pair: tracked by the host (Appendix A12)
       out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d); emit = true;
@@ -770,6 +808,7 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
       pt.ent[sl].freq = nf;
       if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
       else if (old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
+      if (emit) out.serial = pt.serial[sl];
     }
     if (emit) {
       const uint32_t idx = atomicAdd(&ctr->rec_n, 1u);
@@ -841,7 +880,7 @@ __global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {
     uint64_t slot = mix64(e.x) & newt.mask;
     for (;;) {
       uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&newt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(e.x));
-      if (prev == PT_EMPTY) { newt.ent[slot].freq = e.y; break; }
+      if (prev == PT_EMPTY) { newt.ent[slot].freq = e.y; newt.serial[slot] = oldt.serial[s]; break; }
       slot = (slot + 1) & newt.mask;
     }
   }
@@ -907,6 +946,7 @@ class CudaEngine : public Engine {
       CK(cudaHostAlloc(&dp, 8 * sizeof(ull), cudaHostAllocMapped));
       dbg_ = static_cast<ull*>(dp);
     }
+    CK(cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SORT_CAP * sizeof(ull))));
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4, false>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
     if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
@@ -1028,7 +1068,7 @@ class CudaEngine : public Engine {
     DevCounters zero; std::memset(&zero, 0, sizeof zero);
     WordTable wt; std::memset(&wt, 0, sizeof wt);
     uint32_t N = 0; ull n_tokens = 0;
-    uint64_t cap = next_pow2(n / 16 + 1); if (cap < (1u << 16)) cap = 1u << 16;
+    uint64_t cap = next_pow2(n / 64 + 1); if (cap < (1u << 16)) cap = 1u << 16;  // grown 4x and redone if more than half fills up
     uint32_t seed = 0x5bd1e995u;
     for (int attempt = 0;; ++attempt) {
       if (attempt > 8) { std::fprintf(stderr, "[ERROR]\t unique-word table did not converge\n"); return -1; }
@@ -1089,7 +1129,8 @@ class CudaEngine : public Engine {
       k_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, bcnt);
       k_scan4096<<<1, 1024, 0, st_>>>(bcnt, bstart);
       k_scatter<<<grid_for(N, 256), 256, 0, st_>>>(wt, u_slot, N, bstart, cursor, tmp_slot, tmp_first);
-      k_rank<<<grid_for(N, 128), 128, 0, st_>>>(wt, tmp_slot, tmp_first, N, bstart, order_slot);
+      k_sort_buckets<<<4096, SORT_THREADS, SORT_CAP * sizeof(ull), st_>>>(tmp_slot, tmp_first, bstart, order_slot);
+      k_rank_big<<<grid_for(N, 128), 128, 0, st_>>>(wt, tmp_slot, tmp_first, N, bstart, order_slot); launches_++;  // only buckets above SORT_CAP do work
       k_hist_words<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, d_hist, wcnt_, wlen_, len1);
       k_scan_sums<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums);
       k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(sums, nb_scan, sums + nb_scan);
@@ -1204,6 +1245,7 @@ class CudaEngine : public Engine {
   }
   int alloc_pt(PairTable* pt, uint64_t cap) {
     CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->ent), cap * sizeof(PairEnt), st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->serial), cap * 4, st_));
     pt->cap = cap; pt->mask = cap - 1;
     CK(cudaMemsetAsync(pt->ent, 0xFF, cap * sizeof(PairEnt), st_));  // key = EMPTY; freq is written when the entry is claimed
     return 0;
@@ -1215,7 +1257,7 @@ class CudaEngine : public Engine {
     RC(alloc_pt(&nt, cap));
     k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
     CK(cudaStreamSynchronize(st_));
-    cudaFreeAsync(pt_.ent, st_);
+    cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_);
     pt_ = nt;
     return 0;
   }
@@ -1496,7 +1538,7 @@ class CudaEngine : public Engine {
     cudaSetDevice(dev_);
     release_corpus();
     if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); }
-    if (pt_.ent) cudaFreeAsync(pt_.ent, st_);
+    if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); }
     if (recs_) cudaFreeHost(recs_);
     if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
     if (ctr_) cudaFreeAsync(ctr_, st_);

@@ -21,9 +21,10 @@ struct Rec {
   uint64_t val;
   uint64_t seq;
   uint32_t kind;
-  uint32_t pad;
+  uint32_t serial;  // dense id of the pair in the device table (stable until the next count pass); REC_NO_SERIAL for phantoms
 };
 enum : uint32_t { REC_PUSH = 0, REC_DEMOTE = 1, REC_PHANTOM = 2 };
+constexpr uint32_t REC_NO_SERIAL = 0xFFFFFFFFu;
 
 struct EngineConfig {
   int32_t unk_id;

@@ -67,10 +67,11 @@ TrainerCore::~TrainerCore() {
   delete eng_;
 }
 
-void TrainerCore::sync_mirrors() {
-  abi_->heap.data = heap_.data();
+void TrainerCore::sync_mirrors() {  // Trainer.heap in the reference's layout (rebuilt only if the heap changed)
+  size_t cap = 0;
+  abi_->heap.data = heap_.materialize(&cap);
   abi_->heap.size = heap_.size();
-  abi_->heap.cap = heap_.capacity();
+  abi_->heap.cap = cap;
 }
 
 // ---------------------------------------------------------------------------------------------- load (bpe.cpp:110-185)
@@ -143,7 +144,7 @@ int TrainerCore::load_buffer(const uint8_t* text, size_t n) {
   for (size_t i = 0; i < N; i++) abi_->corpus.words[i] = &placeholder_;
   if (N && eng_->word_counts(abi_->corpus.word_counts) != 0) return -1;
   // bpe.cpp:183 re-initialises the pair table; the heap is left alone (it is reset by bpe_init)
-  version_.clear(); phantom_.clear();
+  version_.clear(); phantom_.clear(); ver_.clear();
   load_wall_ms_ = now_ms() - t0;
   if (!quiet_) std::printf("[DEBUG]\t Character histogram built with %u unique characters.\n", info_.n_distinct);  // bpe.cpp:168
   return 0;
@@ -156,7 +157,7 @@ void TrainerCore::count_bigrams() {
   const Rec* recs = nullptr; size_t n = 0;
   if (!quiet_) std::printf("[INFO]\t Counting bigrams from %zu words...\n", static_cast<size_t>(info_.n_words));
   if (eng_->count_pairs(&recs, &n) != 0) { std::fprintf(stderr, "[ERROR]\t device bigram count failed\n"); return; }
-  version_.clear(); phantom_.clear();
+  version_.clear(); phantom_.clear(); ver_.clear();
   // BIMap iteration order (bpe.cpp:219-227): bucket = fnv1a32(pair) & 4095 ascending, chain = creation order, and a
   // pair is created at its first sighting in scan order (hash.cpp:126-129)  ->  sort by (bucket, seq).
   order_.assign(recs, recs + n);
@@ -165,7 +166,7 @@ void TrainerCore::count_bigrams() {
     if (bx != by) return bx < by;
     return x.seq < y.seq;
   });
-  for (const Rec& r : order_) heap_.push(unpack_key(r.key), r.val, 0);
+  for (const Rec& r : order_) { ver_of(r.serial, r.key) = 0; heap_.push(unpack_key(r.key), r.val, 0, r.serial); }
   if (!quiet_) std::printf("[INFO]\t Added %zu pairs to heap (freq >= %llu)\n", n, static_cast<unsigned long long>(abi_->config.min_pair_freq));
   sync_mirrors();
 }
@@ -180,31 +181,47 @@ void TrainerCore::init() {  // bpe.cpp:98-108
 void TrainerCore::apply_records(const Rec* recs, size_t n) {
   // FreqChangeMap iteration (bpe.cpp:297-298): bucket = key % 1024 ascending; inside a bucket the chain is LIFO by
   // first insertion (prepend at bpe.cpp:36-37)  ->  sort by (key & 1023, seq descending).
-  // one 64-bit sort key per record: bucket in the top bits, inverted sequence below (sequences are < 2^52)
-  sort_keys_.resize(n);
+  // Bucket the records by key & 1023 with intrusive lists (counting sort: a few hundred records over 1024 buckets),
+  // then order each bucket's handful of records by descending sequence.
+  if (bucket_head_.empty()) bucket_head_.assign(1024, -1);
+  next_in_bucket_.resize(n);
   for (size_t i = 0; i < n; i++) {
-    version_.prefetch(recs[i].key);
-    sort_keys_[i] = std::make_pair(((recs[i].key & 1023ull) << 52) | ((~recs[i].seq) & ((1ull << 52) - 1)), static_cast<uint32_t>(i));
+    if (recs[i].serial == REC_NO_SERIAL) version_.prefetch(recs[i].key); else if (recs[i].serial < ver_.size()) __builtin_prefetch(&ver_[recs[i].serial]);
+    const uint32_t b = static_cast<uint32_t>(recs[i].key & 1023u);
+    next_in_bucket_[i] = bucket_head_[b];
+    bucket_head_[b] = static_cast<int32_t>(i);
   }
-  std::sort(sort_keys_.begin(), sort_keys_.end());
+  order_idx_.clear();
+  for (uint32_t b = 0; b < 1024; b++) {
+    int32_t i = bucket_head_[b];
+    if (i < 0) continue;
+    bucket_head_[b] = -1;
+    const size_t start = order_idx_.size();
+    for (; i >= 0; i = next_in_bucket_[i]) {  // insertion sort, descending sequence
+      size_t at = order_idx_.size();
+      order_idx_.push_back(static_cast<uint32_t>(i));
+      while (at > start && recs[order_idx_[at - 1]].seq < recs[i].seq) { order_idx_[at] = order_idx_[at - 1]; --at; }
+      order_idx_[at] = static_cast<uint32_t>(i);
+    }
+  }
   const uint64_t min_freq = abi_->config.min_pair_freq;
-  for (const auto& sk : sort_keys_) {
-    const Rec& r = recs[sk.second];
+  for (const uint32_t ri : order_idx_) {
+    const Rec& r = recs[ri];
     PairKey pk = unpack_key(r.key);
     switch (r.kind) {
       case REC_PUSH: {  // bpe.cpp:308-311
-        uint32_t v = ++version_[r.key];
-        heap_.push(pk, r.val, v);
+        uint32_t v = ++ver_of(r.serial, r.key);
+        heap_.push(pk, r.val, v, r.serial);
         break;
       }
       case REC_DEMOTE:  // bpe.cpp:258 seen from the other side: invalidate now instead of discarding at pop
-        ++version_[r.key];
+        ++ver_of(r.serial, r.key);
         break;
       case REC_PHANTOM: {  // bpe.cpp:303-311 on a pair the device table does not hold
         uint64_t& f = phantom_[r.key];
         int64_t d = static_cast<int64_t>(r.val);
         if (d < 0) { uint64_t ad = static_cast<uint64_t>(-d); f = f >= ad ? f - ad : 0; } else { f += static_cast<uint64_t>(d); }
-        if (f >= min_freq) { uint32_t v = ++version_[r.key]; heap_.push(pk, f, v); }
+        if (f >= min_freq) { uint32_t v = ++version_[r.key]; heap_.push(pk, f, v, REC_NO_SERIAL); }
         break;
       }
       default: break;
@@ -220,11 +237,14 @@ int TrainerCore::merge_batch(int batch_size) {
   int done = 0;
   while (done < batch_size && !heap_.empty()) {
     double h0 = now_ms();
-    version_.prefetch(pack_key(heap_.top().key.first, heap_.top().key.second));  // overlaps the miss with the sift-down
-    BPEHeapEntry top = heap_.pop();
+    {  // start the version lookup of the entry about to be popped: its miss overlaps the sift-down
+      const HeapEnt t = heap_.top();
+      if (t.serial == REC_NO_SERIAL) version_.prefetch(pack_key(t.key.first, t.key.second)); else if (t.serial < ver_.size()) __builtin_prefetch(&ver_[t.serial]);
+    }
+    HeapEnt top = heap_.pop();
     const uint64_t k = pack_key(top.key.first, top.key.second);
-    uint32_t* vp = version_.find(k);
-    const uint32_t cur = vp ? *vp : 0;
+    uint32_t cur;
+    if (top.serial == REC_NO_SERIAL) { uint32_t* vp = version_.find(k); cur = vp ? *vp : 0; } else cur = top.serial < ver_.size() ? ver_[top.serial] : 0;
     if (top.version != cur) { host_heap_ms_ += now_ms() - h0; continue; }  // stale, bpe.cpp:247-250
     if (is_phantom(top.key.first, top.key.second)) {  // recompute_freq == 0, bpe.cpp:53,252-257
       uint64_t* f = phantom_.find(k);
@@ -246,7 +266,7 @@ int TrainerCore::merge_batch(int batch_size) {
                                  static_cast<unsigned long long>(top.freq), new_id, abi_->num_merges + 1);
     h0 = now_ms();
     apply_records(recs, n);
-    ++version_[k];  // bpe.cpp:315-316
+    ++ver_of(top.serial, k);  // bpe.cpp:315-316
     host_heap_ms_ += now_ms() - h0;
     occurrences_ += occ;
     abi_->num_merges++;

@@ -3,6 +3,7 @@
 // Engine for everything that is data parallel.  See trainer_core.cpp for the reference file:line map.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -39,10 +40,17 @@ class TrainerCore {
   Trainer* abi_;
   Engine* eng_;
   ExactHeap heap_;
-  FlatMap<uint32_t> version_;   // pair key -> current version (absent = 0)
+  FlatMap<uint32_t> version_;   // PHANTOM pair key -> current version (absent = 0); phantoms have no device serial
+  std::vector<uint32_t> ver_;   // pair serial -> current version (dense, no hashing on the replay path)
+  uint32_t& ver_of(uint32_t serial, uint64_t key) {
+    if (serial == REC_NO_SERIAL) return version_[key];
+    if (serial >= ver_.size()) ver_.resize(std::max<size_t>(serial + 1, ver_.size() * 2 + 1024), 0u);
+    return ver_[serial];
+  }
   FlatMap<uint64_t> phantom_;   // pair keys containing unk_id -> freq as the reference's table would hold it
   std::vector<Rec> order_;      // scratch: records in application order
-  std::vector<std::pair<uint64_t, uint32_t>> sort_keys_;
+  std::vector<int32_t> bucket_head_, next_in_bucket_;  // scratch of apply_records
+  std::vector<uint32_t> order_idx_;
   LoadInfo info_;
   bool loaded_ = false;
   size_t merge_cap_ = 0;

@@ -99,12 +99,12 @@ class HostSimEngine : public Engine {
       words_.push_back(std::move(ids)); counts_.push_back(ws[i].count);
     }
     info->n_words = ws.size(); info->n_symbols = S; info->n_tokens = ntok;
-    table_.clear();
+    table_.clear(); next_serial_ = 0;
     return 0;
   }
 
   int count_pairs(const Rec** recs, size_t* n) override {
-    table_.clear();
+    table_.clear(); next_serial_ = 0;
     std::unordered_map<uint64_t, std::pair<int64_t, uint64_t>> agg;
     uint64_t p = 0;
     for (size_t wi = 0; wi < words_.size(); wi++) {
@@ -121,8 +121,9 @@ class HostSimEngine : public Engine {
     if (exchange(agg) != 0) return -1;
     out_.clear();
     for (auto& kv : agg) {
-      table_[kv.first] = static_cast<uint64_t>(kv.second.first);
-      if (static_cast<uint64_t>(kv.second.first) >= cfg_.min_freq) out_.push_back(Rec{kv.first, static_cast<uint64_t>(kv.second.first), kv.second.second, REC_PUSH, 0});
+      Ent& e = ent(kv.first);
+      e.freq = static_cast<uint64_t>(kv.second.first);
+      if (e.freq >= cfg_.min_freq) out_.push_back(Rec{kv.first, e.freq, kv.second.second, REC_PUSH, e.serial});
     }
     std::shuffle(out_.begin(), out_.end(), rng_);
     *recs = out_.data(); *n = out_.size();
@@ -165,15 +166,16 @@ class HostSimEngine : public Engine {
     for (auto& kv : agg) {
       int32_t pa = static_cast<int32_t>(kv.first >> 32), pb = static_cast<int32_t>(kv.first & 0xFFFFFFFFu);
       if (pa == A && pb == B) continue;
-      if (pa == cfg_.unk_id || pb == cfg_.unk_id) { out_.push_back(Rec{kv.first, static_cast<uint64_t>(kv.second.first), kv.second.second, REC_PHANTOM, 0}); continue; }
-      uint64_t& f = table_[kv.first];
+      if (pa == cfg_.unk_id || pb == cfg_.unk_id) { out_.push_back(Rec{kv.first, static_cast<uint64_t>(kv.second.first), kv.second.second, REC_PHANTOM, REC_NO_SERIAL}); continue; }
+      Ent& e = ent(kv.first);
+      uint64_t& f = e.freq;
       uint64_t old = f;
       int64_t d = kv.second.first;
       if (d < 0) { uint64_t ad = static_cast<uint64_t>(-d); f = f >= ad ? f - ad : 0; } else f += static_cast<uint64_t>(d);
-      if (f >= cfg_.min_freq) out_.push_back(Rec{kv.first, f, kv.second.second, REC_PUSH, 0});
-      else if (old >= cfg_.min_freq) out_.push_back(Rec{kv.first, f, kv.second.second, REC_DEMOTE, 0});
+      if (f >= cfg_.min_freq) out_.push_back(Rec{kv.first, f, kv.second.second, REC_PUSH, e.serial});
+      else if (old >= cfg_.min_freq) out_.push_back(Rec{kv.first, f, kv.second.second, REC_DEMOTE, e.serial});
     }
-    table_[fc_key(A, B)] = 0;
+    ent(fc_key(A, B)).freq = 0;
     std::shuffle(out_.begin(), out_.end(), rng_);
     *recs = out_.data(); *n = out_.size(); *occurrences = occ;
     return 0;
@@ -202,7 +204,7 @@ class HostSimEngine : public Engine {
   }
   uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) override {
     uint64_t i = 0;
-    for (auto& kv : table_) { if (i < cap) { ab[2 * i] = static_cast<int32_t>(kv.first >> 32); ab[2 * i + 1] = static_cast<int32_t>(kv.first & 0xFFFFFFFFu); freq[i] = kv.second; } i++; }
+    for (auto& kv : table_) { if (i < cap) { ab[2 * i] = static_cast<int32_t>(kv.first >> 32); ab[2 * i + 1] = static_cast<int32_t>(kv.first & 0xFFFFFFFFu); freq[i] = kv.second.freq; } i++; }
     return i;
   }
   void stats(EngineStats* out) override { std::memset(out, 0, sizeof *out); out->pair_entries = table_.size(); }
@@ -215,7 +217,10 @@ class HostSimEngine : public Engine {
   std::vector<std::vector<int32_t>> words_;
   std::vector<uint64_t> counts_, all_counts_;
   int rank_ = 0, world_ = 1;
-  std::unordered_map<uint64_t, uint64_t> table_;
+  struct Ent { uint64_t freq = 0; uint32_t serial = REC_NO_SERIAL; };
+  std::unordered_map<uint64_t, Ent> table_;
+  Ent& ent(uint64_t k) { Ent& e = table_[k]; if (e.serial == REC_NO_SERIAL) e.serial = next_serial_++; return e; }
+  uint32_t next_serial_ = 0;
   std::vector<Rec> out_;
   std::mt19937_64 rng_{12345};
 };
