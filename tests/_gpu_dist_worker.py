@@ -21,12 +21,13 @@ for name in sys.argv[5:]:
     data = corpus_bytes(case)
     t = BPETrainer(*case["config"])
     t.load_bytes(data)
+    slots_at_load = t.stats()["n_slots"]
     n = t.train()
     mb = b"".join(struct.pack("<3i", *m) for m in t.merges())
     model, vocab = out_path + ".model", out_path + ".vocab"
     t.save(model, vocab)
     st = t.stats()
     results[name] = {"merges": n, "n_words": t.num_words, "merges_md5": md5(mb), "vocab_md5": md5(open(vocab, "rb").read()),
-                     "model_ok": open(model, "rb").read() == mb, "local_slots": st["n_slots"], "occurrences": st["occurrences"]}
+                     "model_ok": open(model, "rb").read() == mb, "local_slots": slots_at_load, "occurrences": st["occurrences"]}
     t.destroy()
 json.dump(results, open(out_path, "w"))

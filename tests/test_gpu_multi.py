@@ -37,7 +37,7 @@ def _run(world, native):
         assert len({r[name]["occurrences"] for r in res}) == 1          # global occurrence counts agree
         if case["n_words"] > 1000:
             slots = [r[name]["local_slots"] for r in res]
-            assert max(slots) < 1.2 * (sum(slots) / len(slots)) + 64     # shards are balanced by symbol slots
+            assert max(slots) < 1.1 * (sum(slots) / len(slots)) + 64     # shards are balanced by symbol slots (measured right after load)
 
 
 def test_two_gpus(native):
