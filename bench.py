@@ -254,6 +254,8 @@ def main():
     scan_ms = sum(s[3]["dense_device_ms"] for s in steps)
     scan_bytes = sum(s[3]["dense_bytes"] for s in steps)
     scan_n = sum(s[3]["dense_launches"] for s in steps)
+    dense_phase_ms = sum(s[3]["dense_phase_ms"] for s in steps)
+    all_phase_ms = sum(s[3]["scan_phase_ms"] for s in steps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -268,14 +270,19 @@ def main():
         "e2e": {"value": total_merges / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]) + 8 * merges,
                 "load_s_per_step": sum(s[1] for s in steps) / args.steps, "train_s_per_step": sum(s[2] for s in steps) / args.steps},
         "gpu_launches": int(sum(s[3]["kernel_launches"] for s in steps)),
-        "roofline": {"bound": "hbm", "kernel": "k_detect (per-merge scan of the symbol array)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_merge<4,false> (one cooperative launch per merge: scan | barrier | fold + publish | rewrite)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "launches_timed": int(scan_n), "avg_launch_us": 1e3 * scan_ms / scan_n if scan_n else None,
                      "bytes_per_launch": scan_bytes / scan_n if scan_n else None,
-                     "note": "achieved/frac = timed k_scan_merge launches that streamed >= 90 % of the symbol array (no tile skipped): 4*slots bytes / CUDA-event "
-                             "duration, which includes the kernel's delta emission and last-CTA finalize tail; 'all_launches' = every timed launch incl. tile-skipping ones "
+                     "note": "achieved/frac = timed k_merge launches that streamed >= 90 % of the symbol array (no tile skipped): 4*slots bytes / CUDA-event "
+                             "duration, which includes the kernel's delta emission, pair-table fold and rewrite phases; 'all_launches' = every timed launch incl. tile-skipping ones "
                              "(effective = algorithmic 4*slots bytes / duration, touched = bytes of candidate tiles actually read / duration)",
+                     "scan_phase": {"how": "in-kernel %globaltimer from kernel start to the end of the scan phase (first grid barrier), dense launches",
+                                    "achieved": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 if dense_phase_ms else None,
+                                    "frac": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 / peak if dense_phase_ms and peak else None,
+                                    "avg_us": 1e3 * dense_phase_ms / scan_n if scan_n else None,
+                                    "all_launches_avg_us": 1e3 * all_phase_ms / all_n if all_n else None},
                      "all_launches": {"n": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
                                       "effective_gbs": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else None,
                                       "touched_gbs": all_touched / (all_ms * 1e-3) / 1e9 if all_ms else None,

@@ -114,6 +114,7 @@ typedef struct shred_stats_t {
   double scan_bytes_touched;     /* bytes of the symbol array the timed scans actually read (candidate tiles) */
   uint64_t dense_launches; double dense_device_ms; double dense_bytes; /* timed scans that streamed >= 90 % of the array */
   uint64_t cand_tiles, tiles_total; /* candidate / total tiles summed over all merges of the last train */
+  double scan_phase_ms, dense_phase_ms; /* in-kernel timer: start -> end of the scan phase, all / dense timed launches */
   uint64_t h2d_bytes, d2h_bytes;
 } shred_stats_t;
 SHRED_API int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);

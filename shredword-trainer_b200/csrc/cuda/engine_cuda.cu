@@ -93,6 +93,7 @@ struct DevCounters {  // device memory
   ull n_tokens;
   uint32_t n_unique, blocks_done2;
   uint32_t cand_tiles, bar;
+  uint32_t sent_ctas, pad4;
 };
 
 struct DeltaTable {
@@ -640,10 +641,12 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uin
   __syncthreads();
 }
 
-// Cooperative exchange of the delta table's dense list (klist/list/delta/seq) between ranks: 3 grid barriers.
+// Cooperative exchange of the delta table's dense list (klist/list/delta/seq) between ranks.  Must be entered after a
+// grid barrier (the local list is complete); ends with one grid barrier (number `barrier_no` of this launch).
 // On return the local delta table holds the GLOBAL aggregate and *occ_global the global occurrence count.
-__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, uint32_t bar_base, int first_barrier, ull occ_local,
+__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, uint32_t bar_base, int barrier_no, ull occ_local,
                                                 ull* occ_global) {
+  __shared__ bool last_sender;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   const uint32_t n_local = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
   if (n_local > INBOX_ENTRIES && gtid == 0) atomicOr(&ctr->err, ERR_INBOX_FULL);
@@ -657,8 +660,12 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
     }
   }
   __threadfence_system();
-  grid_barrier(&ctr->bar, bar_base + (first_barrier + 0) * gridDim.x, &ctr->err);
-  if (gtid == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) last_sender = atomicAdd(&ctr->sent_ctas, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out: announce the list to the peers
+    __threadfence();
+    ctr->sent_ctas = 0;
     for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
       InboxHdr* h = reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank));
       h->n = n_send; h->aux = occ_local;
@@ -666,14 +673,19 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
     __threadfence_system();
     for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
       *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
+  }
+  if (threadIdx.x == 0) {  // every CTA waits for the peers' lists to land in MY inbox (local memory)
     const long long t0 = clock64();
-    for (int src = 0; src < D.world; src++) if (src != D.rank) {  // wait for every peer's list to land in MY inbox
+    for (int src = 0; src < D.world; src++) if (src != D.rank) {
       volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
-      while (*f != D.xseq) if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }  // ~4 s: never hang the GPU
+      while (*f != D.xseq) {
+        __nanosleep(64);  // hundreds of CTAs poll this line while the peer's NVLink write has to get in
+        if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }  // ~4 s: never hang the GPU
+      }
     }
     __threadfence_system();
   }
-  grid_barrier(&ctr->bar, bar_base + (first_barrier + 1) * gridDim.x, &ctr->err);
+  __syncthreads();
   ull occ = occ_local;
   for (int src = 0; src < D.world; src++) if (src != D.rank) {  // fold the peers' entries into my delta table
     const uint8_t* reg = inbox_region(D.peer[D.rank], D.world, D.xseq, src);
@@ -685,14 +697,14 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
       dt_add(dt, ctr, __ldcv(e + 3 * i), static_cast<int64_t>(__ldcv(e + 3 * i + 1)), __ldcv(e + 3 * i + 2));
   }
   *occ_global = occ;
-  grid_barrier(&ctr->bar, bar_base + (first_barrier + 2) * gridDim.x, &ctr->err);
+  grid_barrier(&ctr->bar, bar_base + barrier_no * gridDim.x, &ctr->err);
 }
 
 // count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
 __global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
                                                              uint64_t flag_value, DistArgs D, uint32_t bar_base) {
   ull occ;
-  exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);
+  exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
   if (blockIdx.x == 0) finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
 }
 
@@ -969,10 +981,13 @@ class CudaEngine : public Engine {
     CK(cudaEventCreate(&evm1_));
     cudaMemPool_t pool;  // stream-ordered allocations; keep freed blocks cached so repeated loads do not pay cudaMalloc
     if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
-    if (const char* d = std::getenv("SHRED_DEBUG_TIMING")) if (*d && *d != '0') {
+    {  // in-kernel phase timestamps (%globaltimer) of the timed launches
       void* dp = nullptr;
       CK(cudaHostAlloc(&dp, 8 * sizeof(ull), cudaHostAllocMapped));
       dbg_ = static_cast<ull*>(dp);
+      std::memset(dp, 0, 8 * sizeof(ull));
+      const char* d = std::getenv("SHRED_DEBUG_TIMING");
+      dbg_print_ = d && *d && *d != '0';
     }
     CK(cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SORT_CAP * sizeof(ull))));
     int nb = 0;
@@ -1326,7 +1341,7 @@ class CudaEngine : public Engine {
         uint32_t a_reccap = rec_cap_, a_bar = bar_count_;
         Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
         uint64_t a_flag = flag_;
-        bar_count_ += 3u * static_cast<uint32_t>(grid);
+        bar_count_ += 1u * static_cast<uint32_t>(grid);
         void* args[] = {&dt_, &pt_, &ctr_, &recs_, &a_reccap, &a_ctrl, &P_, &a_flag, &a_D, &a_bar};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_count_finalize), dim3(grid), dim3(256), args, 0, st_));
       } else {
@@ -1360,8 +1375,7 @@ class CudaEngine : public Engine {
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
     if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
-    if (dbg_) { dbg_[0] = dbg_[1] = dbg_[2] = dbg_[3] = dbg_[4] = 0; }
-    const double th0 = now_ms();
+    ull* a_dbg = timed ? dbg_ : nullptr;
     const uint32_t n_tiles = static_cast<uint32_t>((n_slots_ + TILE_SLOTS - 1) >> TILE_SHIFT);
     int grid = detect_grid(n4);
     const uint32_t tiles_per_cta = (n_tiles + grid - 1) / grid;
@@ -1378,9 +1392,9 @@ class CudaEngine : public Engine {
       uint32_t a_bar = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
       DistArgs a_D = dist_;
       if (world_ > 1) a_D = next_exchange();
-      bar_count_ += (world_ > 1 ? 4u : 1u) * static_cast<uint32_t>(grid);
+      bar_count_ += (world_ > 1 ? 2u : 1u) * static_cast<uint32_t>(grid);
       void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
-                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &dbg_, &a_D};
+                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &a_dbg, &a_D};
       CK(cudaLaunchCooperativeKernel(world_ > 1 ? reinterpret_cast<void*>(k_merge<4, true>) : reinterpret_cast<void*>(k_merge<4, false>), dim3(grid), dim3(256), args,
                                      0, st_));
     }
@@ -1388,14 +1402,6 @@ class CudaEngine : public Engine {
     launches_ += 1;
     launch_ms_ += now_ms() - tl0;
     RC(wait_flag());
-    if (dbg_) {
-      cudaStreamSynchronize(st_);
-      dbg_acc_[0] += (dbg_[1] - dbg_[0]) * 1e-3; dbg_acc_[1] += (dbg_[2] - dbg_[1]) * 1e-3; dbg_acc_[2] += (dbg_[3] - dbg_[2]) * 1e-3;
-      dbg_acc_[4] += (now_ms() - th0) * 1e3; dbg_n_++;
-      if ((dbg_n_ % 2000) == 0 || dbg_n_ == 50)
-        std::fprintf(stderr, "[KTIME]\t merges %llu: scan+emit+barrier %.1f us, finalize+publish %.1f us, rewrite+rearm %.1f us | host launch->kernel end %.1f us (avg per merge)\n",
-                     (unsigned long long)dbg_n_, dbg_acc_[0] / dbg_n_, dbg_acc_[1] / dbg_n_, dbg_acc_[2] / dbg_n_, dbg_acc_[4] / dbg_n_);
-    }
     if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
     if (timed) {
       float ms = 0;
@@ -1403,7 +1409,13 @@ class CudaEngine : public Engine {
       cudaEventElapsedTime(&ms, ev0_, ev1_);
       const double algo = 4.0 * static_cast<double>(n4) * 4.0, touched = 4.0 * TILE_SLOTS * static_cast<double>(ctrl_->cand_tiles);
       es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += algo; es_.scan_bytes_touched += touched;
-      if (ctrl_->cand_tiles * 10 >= static_cast<uint64_t>(n_tiles) * 9) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; }  // streams >= 90 % of the array
+      const double p1 = (dbg_[1] - dbg_[0]) * 1e-6, p2 = (dbg_[2] - dbg_[1]) * 1e-6, p3 = (dbg_[3] - dbg_[2]) * 1e-6;  // ms: scan+emit+barrier | fold+publish | rewrite
+      es_.scan_phase_ms += p1;
+      if (ctrl_->cand_tiles * 10 >= static_cast<uint64_t>(n_tiles) * 9) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; es_.dense_phase_ms += p1; }  // streams >= 90 % of the array
+      dbg_acc_[0] += p1; dbg_acc_[1] += p2; dbg_acc_[2] += p3; dbg_acc_[3] += ms; dbg_n_++;
+      if (dbg_print_ && (dbg_n_ % 500) == 0)
+        std::fprintf(stderr, "[KTIME]\t %llu timed merges: scan+emit+barrier %.1f us, fold+publish %.1f us, rewrite+rearm %.1f us | kernel (events) %.1f us (averages)\n",
+                     (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
     }
     cand_tiles_total_ += ctrl_->cand_tiles; tiles_total_ += n_tiles;
     *n = ctrl_->n_recs; *occurrences = ctrl_->occ;
@@ -1624,6 +1636,7 @@ class CudaEngine : public Engine {
   double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0;
   int timing_every_ = 0;
   ull* dbg_ = nullptr;
+  bool dbg_print_ = false;
   double dbg_acc_[5] = {0, 0, 0, 0, 0};
   uint64_t dbg_n_ = 0;
   int scan_ctas_per_sm_ = 4;

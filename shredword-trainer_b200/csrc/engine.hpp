@@ -44,6 +44,7 @@ struct EngineStats {
   uint64_t n_slots, n_symbols_live, pair_entries, compactions;
   uint64_t scan_launches; double scan_device_ms; double scan_bytes; double scan_bytes_touched;
   uint64_t dense_launches; double dense_device_ms; double dense_bytes;  // timed scans that streamed >= 90 % of the array
+  double scan_phase_ms, dense_phase_ms;  // in-kernel %globaltimer: kernel start -> end of the scan phase (all timed / dense timed launches)
   uint64_t cand_tiles, tiles_total;
   uint64_t count_launches; double count_device_ms; double count_bytes;
   uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;

@@ -356,7 +356,7 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->merges = merges_last_; s->occurrences = occurrences_;
   s->scan_launches = es.scan_launches; s->scan_device_ms = es.scan_device_ms; s->scan_bytes = es.scan_bytes;
   s->scan_bytes_touched = es.scan_bytes_touched; s->dense_launches = es.dense_launches; s->dense_device_ms = es.dense_device_ms; s->dense_bytes = es.dense_bytes;
-  s->cand_tiles = es.cand_tiles; s->tiles_total = es.tiles_total;
+  s->cand_tiles = es.cand_tiles; s->tiles_total = es.tiles_total; s->scan_phase_ms = es.scan_phase_ms; s->dense_phase_ms = es.dense_phase_ms;
   s->count_launches = es.count_launches; s->count_device_ms = es.count_device_ms; s->count_bytes = es.count_bytes;
   s->ingest_launches = es.ingest_launches; s->ingest_device_ms = es.ingest_device_ms; s->ingest_bytes = es.ingest_bytes;
   s->kernel_launches = es.kernel_launches;
