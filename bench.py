@@ -237,6 +237,13 @@ def main():
     wall = time.perf_counter() - wall0
     clocks = sampler.finish()
 
+    # informational: the same load through bpe_load_corpus(path) (file in the page cache -> mmap -> HBM), outside the timed region
+    load_file_s = None
+    if world == 1:
+        with quiet:
+            tf = BPETrainer(vocab, unk, cov, mf)
+            t0 = time.perf_counter(); tf.load_corpus(corpus); load_file_s = time.perf_counter() - t0
+            tf.destroy()
     merges = steps[0][0]
     train_dev_ms = sum(s[3]["train_device_ms"] for s in steps)
     e2e_s = sum(s[1] + s[2] for s in steps)
@@ -292,7 +299,7 @@ def main():
                    "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
                    "ingest_device_ms": st["ingest_device_ms"], "ingest_gbs": st["ingest_bytes"] / (st["ingest_device_ms"] * 1e-3) / 1e9 if st["ingest_device_ms"] else None,
                    "count_device_ms": st["count_device_ms"], "count_gbs": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 if st["count_device_ms"] else None,
-                   "h2d_ms": st["h2d_ms"], "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
+                   "h2d_ms": st["h2d_ms"], "load_corpus_from_file_s": load_file_s, "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
     }
     try:

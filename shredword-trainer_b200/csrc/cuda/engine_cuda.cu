@@ -427,7 +427,11 @@ __device__ __forceinline__ void cnt_add(ull* s_key, ull* s_sum, ull* s_seq, cons
   for (uint32_t probe = 0; probe < CNT_PROBES; ++probe) {
     ull cur = s_key[slot];
     if (cur == ~0ull) { const ull prev = atomicCAS(&s_key[slot], ~0ull, static_cast<ull>(key)); cur = prev == ~0ull ? key : prev; }
-    if (cur == key) { atomicAdd(&s_sum[slot], static_cast<ull>(c)); atomicMin(&s_seq[slot], static_cast<ull>(seq)); return; }
+    if (cur == key) {
+      atomicAdd(&s_sum[slot], static_cast<ull>(c));
+      if (seq < *reinterpret_cast<volatile ull*>(&s_seq[slot])) atomicMin(&s_seq[slot], static_cast<ull>(seq));  // positions grow along the grid-stride loop: rarely taken
+      return;
+    }
     slot = (slot + 1) & (CNT_SLOTS - 1);
   }
   dt_add(dt, ctr, key, static_cast<int64_t>(c), seq);  // shared table crowded: straight to the global one
@@ -1363,6 +1367,7 @@ class CudaEngine : public Engine {
   int merge(int32_t a, int32_t b, int32_t new_id, const Rec** recs, size_t* n, uint64_t* occurrences) override {
     *recs = recs_; *n = 0; *occurrences = 0;
     const double tm0 = now_ms();
+    CK(cudaSetDevice(dev_));  // the caller's thread may have another current device
     // keep the pair table at most half full even if this merge creates every key it can (4 per distinct id)
     const uint64_t worst_new = 4ull * (static_cast<uint64_t>(new_id) + 2);
     if ((pt_n_ + worst_new) * 2 > pt_.cap) RC(grow_pt(pt_n_ + worst_new));

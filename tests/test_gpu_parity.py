@@ -227,3 +227,18 @@ def test_size_independent_properties_at_scale(T, tmp_path):
     ov = tmp_path / "ov"; o.save(str(tmp_path / "om"), str(ov))
     assert ov.read_bytes() == vocab.read_bytes() and len(lines) > 256
     t.destroy(); o.destroy()
+
+
+def test_two_trainers_interleaved(T):
+    """independent trainers are independent (reference: no globals): interleave their step-wise calls"""
+    da = open(os.path.join(os.path.dirname(__file__), "golden", "kat_cpp.txt"), "rb").read()
+    db = open(os.path.join(os.path.dirname(__file__), "golden", "kat_py.txt"), "rb").read()
+    a, b = T(300, -1, 0.99, 2), T(300, 0, 0.995, 2)
+    a.load_bytes(da); b.load_bytes(db); a.init(); b.init()
+    for _ in range(44):
+        assert a.merge_batch(1) == 1
+        assert b.merge_batch(1) == 1
+    ga = [c for c in GOLDEN if c["name"] == "kat_cpp"][0]
+    gb = [c for c in GOLDEN if c["name"] == "kat_py"][0]
+    assert md5(_merge_bytes(a.merges())) == ga["merges_md5"] and md5(_merge_bytes(b.merges())) == gb["merges_md5"]
+    a.destroy(); b.destroy()
