@@ -244,6 +244,19 @@ def main():
             tf = BPETrainer(vocab, unk, cov, mf)
             t0 = time.perf_counter(); tf.load_corpus(corpus); load_file_s = time.perf_counter() - t0
             tf.destroy()
+    # informational (N>1, sharded default): the same GPUs as N independent replicas -- one full trainer per GPU, no exchange
+    replicas = None
+    if sharded:
+        saved = {k: os.environ.pop(k) for k in ("SHRED_RANK", "SHRED_WORLD")}
+        barrier()
+        with quiet:
+            rstep = one_step()
+        barrier()
+        os.environ.update(saved)
+        rt = torch.tensor([rstep[3]["train_device_ms"], rstep[1] + rstep[2]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        replicas = {"what": f"{world} independent trainers (one per GPU) on the same workload, 1 step, max over ranks",
+                    "value": world * rstep[0] / (rt[0].item() * 1e-3), "e2e": world * rstep[0] / rt[1].item(), "unit": "merges/s", "scaling": "weak"}
     merges = steps[0][0]
     train_dev_ms = sum(s[3]["train_device_ms"] for s in steps)
     e2e_s = sum(s[1] + s[2] for s in steps)
@@ -302,6 +315,8 @@ def main():
                    "h2d_ms": st["h2d_ms"], "load_corpus_from_file_s": load_file_s, "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
     }
+    if replicas:
+        line["detail"]["replicas"] = replicas
     try:
         big = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"].get(args.workload)
         if big:
