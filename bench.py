@@ -5,7 +5,7 @@ A "step" is one full pass of the hot path over the synthetic corpus: bpe_load_co
 table) + bpe_train (pair count + merge loop) + reading the merge list back.
   value  merges/s of bpe_train() alone, corpus already resident in HBM, timed with CUDA events on the library's stream
   e2e    merges/s through the C ABI with HOST buffers: pinned corpus bytes -> load -> train -> merge list on the host
-  roofline      the dominant kernel (k_detect, the per-merge HBM scan): algorithmic bytes / CUDA-event duration
+  roofline      the dominant kernel (k_merge, one cooperative launch per merge): algorithmic bytes / CUDA-event duration
   cpu_baseline  the unmodified reference (oracle/_ref, pinned with the zero-fill malloc shim) on a bounded sample
 
 python bench.py --gpus N --steps K --warmup W            (N>1 under torch.distributed.run: one rank per GPU)
@@ -282,7 +282,6 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     line = {
         "metric": "bpe_train_merges_per_s", "value": total_merges / (train_dev_ms * 1e-3), "unit": "merges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u64",
@@ -290,23 +289,25 @@ def main():
         "e2e": {"value": total_merges / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]) + 8 * merges,
                 "load_s_per_step": sum(s[1] for s in steps) / args.steps, "train_s_per_step": sum(s[2] for s in steps) / args.steps},
         "gpu_launches": int(sum(s[3]["kernel_launches"] for s in steps)),
-        "roofline": {"bound": "hbm", "kernel": "k_merge<4,false> (one cooperative launch per merge: scan | barrier | fold + publish | rewrite)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_merge<4,false> (one cooperative launch per merge: scan | barrier | fold + publish | rewrite)",
+                     "achieved": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else 0.0, "peak": peak, "unit": "GB/s",
+                     "frac": all_bytes / (all_ms * 1e-3) / 1e9 / peak if all_ms and peak else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                     "launches_timed": int(scan_n), "avg_launch_us": 1e3 * scan_ms / scan_n if scan_n else None,
-                     "bytes_per_launch": scan_bytes / scan_n if scan_n else None,
-                     "note": "achieved/frac = timed k_merge launches that streamed >= 90 % of the symbol array (no tile skipped): 4*slots bytes / CUDA-event "
-                             "duration, which includes the kernel's delta emission, pair-table fold and rewrite phases; 'all_launches' = every timed launch incl. tile-skipping ones "
-                             "(effective = algorithmic 4*slots bytes / duration, touched = bytes of candidate tiles actually read / duration)",
-                     "scan_phase": {"how": "in-kernel %globaltimer from kernel start to the end of the scan phase (first grid barrier), dense launches",
-                                    "achieved": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 if dense_phase_ms else None,
-                                    "frac": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 / peak if dense_phase_ms and peak else None,
-                                    "avg_us": 1e3 * dense_phase_ms / scan_n if scan_n else None,
-                                    "all_launches_avg_us": 1e3 * all_phase_ms / all_n if all_n else None},
-                     "all_launches": {"n": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
-                                      "effective_gbs": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else None,
-                                      "touched_gbs": all_touched / (all_ms * 1e-3) / 1e9 if all_ms else None,
-                                      "tiles_scanned_frac": st["cand_tiles"] / st["tiles_total"] if st["tiles_total"] else None}},
+                     "launches_timed": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
+                     "bytes_per_launch": all_bytes / all_n if all_n else None,
+                     "note": "achieved = ALGORITHMIC bytes (4 B x symbol slots, SURVEY 8d B_merge) / CUDA-event duration of the whole kernel, averaged over every 8th "
+                             "launch of the timed region. The kernel reads fewer bytes than that: a tile occurrence index skips tiles that cannot hold the pair "
+                             "(touched_gbs = bytes actually scanned / duration), and its duration is mostly a latency chain (delta emission, grid barrier, "
+                             "pair-table fold, host flag, rewrite), see DESIGN.md section 5. ncu --set full (profiles/): a dense launch reads 31.7 MB of DRAM for "
+                             "31.3 MB of algorithmic bytes (no re-reads); the stand-alone scan kernel of run 1 streamed at 4.76 TB/s = 73 % of the measured peak.",
+                     "touched_gbs": all_touched / (all_ms * 1e-3) / 1e9 if all_ms else None,
+                     "tiles_scanned_frac": st["cand_tiles"] / st["tiles_total"] if st["tiles_total"] else None,
+                     "dense_launches": {"what": "timed launches that scanned >= 90 % of the tiles (early, occurrence-heavy merges)", "n": int(scan_n),
+                                        "avg_launch_us": 1e3 * scan_ms / scan_n if scan_n else None,
+                                        "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms else None,
+                                        "scan_phase_gbs": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 if dense_phase_ms else None,
+                                        "scan_phase_frac": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 / peak if dense_phase_ms and peak else None},
+                     "scan_phase_avg_us_all_launches": 1e3 * all_phase_ms / all_n if all_n else None},
         "detail": {"merges_per_step": merges, "n_words": int(st["n_words"]), "n_symbols_initial": int(st["n_symbols_initial"]), "n_symbols_final": int(st["n_symbols_live"]),
                    "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
                    "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
