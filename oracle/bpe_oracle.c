@@ -22,10 +22,15 @@
  *   train loop / stop conditions ............. bpe.cpp:345-386
  *   save (vocab text + model int32 triples) .. bpe.cpp:388-432
  */
+#define _GNU_SOURCE
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #define ORA_BASE_VOCAB 256      /* bpe.h:20 INITIAL_VOCAB_SIZE */
 #define ORA_WORD_BUCKETS 4096   /* bpe.h:21 INITIAL_STR_BUFFER, used as StrMap bucket count (bpe.cpp:116) */
@@ -260,16 +265,20 @@ int oracle_load_buffer(void *h, const uint8_t *text, size_t n) {
 
 int oracle_load(void *h, const char *path) {
   if (!h || !path) return -1; /* bpe.cpp:111-114 */
-  FILE *f = fopen(path, "rb");
-  if (!f) return -1; /* bpe.cpp:118-122 */
-  fseek(f, 0, SEEK_END);
-  long n = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  uint8_t *buf = (uint8_t *)xmalloc((size_t)n + 1);
-  size_t got = fread(buf, 1, (size_t)n, f);
-  fclose(f);
-  int rc = oracle_load_buffer(h, buf, got);
-  free(buf);
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return -1; /* bpe.cpp:118-122 */
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); return -1; }
+  size_t n = (size_t)st.st_size;
+  int rc;
+  if (n == 0) rc = oracle_load_buffer(h, (const uint8_t *)"", 0);
+  else { /* map instead of read: a 50 GB corpus then costs page cache, not heap */
+    void *p = mmap(NULL, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p == MAP_FAILED) { close(fd); return -1; }
+    rc = oracle_load_buffer(h, (const uint8_t *)p, n);
+    munmap(p, n);
+  }
+  close(fd);
   return rc;
 }
 

@@ -1004,6 +1004,7 @@ class CudaEngine : public Engine {
       if (world_ > MAX_RANKS || rank_ < 0 || rank_ >= world_) { std::fprintf(stderr, "[ERROR]\t bad SHRED_RANK/SHRED_WORLD (%d/%d, at most %d ranks)\n", rank_, world_, MAX_RANKS); return -1; }
       RC(dist_setup());
     } else { world_ = 1; rank_ = 0; }
+    if (const char* pl = std::getenv("SHRED_PLAIN_LAUNCH")) plain_launch_ = *pl && *pl != '0';
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     return 0;
@@ -1400,8 +1401,9 @@ class CudaEngine : public Engine {
       bar_count_ += (world_ > 1 ? 2u : 1u) * static_cast<uint32_t>(grid);
       void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
                       &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &a_dbg, &a_D};
-      CK(cudaLaunchCooperativeKernel(world_ > 1 ? reinterpret_cast<void*>(k_merge<4, true>) : reinterpret_cast<void*>(k_merge<4, false>), dim3(grid), dim3(256), args,
-                                     0, st_));
+      const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<4, true>) : reinterpret_cast<const void*>(k_merge<4, false>);
+      if (plain_launch_) CK(cudaLaunchKernel(kfn, dim3(grid), dim3(256), args, 0, st_));  // experiment: same grid, no co-residency check by the driver
+      else CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
     }
     if (timed) CK(cudaEventRecord(ev1_, st_));
     launches_ += 1;
@@ -1641,7 +1643,7 @@ class CudaEngine : public Engine {
   double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0;
   int timing_every_ = 0;
   ull* dbg_ = nullptr;
-  bool dbg_print_ = false;
+  bool dbg_print_ = false, plain_launch_ = false;
   double dbg_acc_[5] = {0, 0, 0, 0, 0};
   uint64_t dbg_n_ = 0;
   int scan_ctas_per_sm_ = 4;
