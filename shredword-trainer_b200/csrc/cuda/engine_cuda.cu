@@ -34,7 +34,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 
 #include "../charset.hpp"
 #include "../engine.hpp"
@@ -1080,7 +1084,13 @@ class CudaEngine : public Engine {
   DistArgs next_exchange() { DistArgs d = dist_; d.xseq = ++dist_.xseq; return d; }
 
   // ---------------------------------------------------------------------------------------------------------- load
-  int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) override {
+  int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) override { return load_impl(text, -1, n, cfg, info); }
+
+  // bpe_load_corpus(path): the file goes to HBM through a ring of pinned staging buffers, one reader thread per buffer
+  // (pread from the page cache) while the previous chunks are already in flight over PCIe.
+  int load_file(int fd, size_t n, const EngineConfig& cfg, LoadInfo* info) override { return load_impl(nullptr, fd, n, cfg, info); }
+
+  int load_impl(const uint8_t* text, int fd, size_t n, const EngineConfig& cfg, LoadInfo* info) {
     CK(cudaSetDevice(dev_));
     cfg_ = cfg;
     vocab_hint_ = cfg.vocab_size < (1ull << 22) ? cfg.vocab_size : (1ull << 22);
@@ -1095,7 +1105,8 @@ class CudaEngine : public Engine {
     uint8_t* d_text = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&d_text), padded, st_));
     double t0 = now_ms();
-    if (n) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
+    if (n && text) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
+    if (n && !text && stream_file(fd, n, d_text) != 0) { cudaFreeAsync(d_text, st_); return -1; }
     CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
     CK(cudaStreamSynchronize(st_));
     es_.h2d_ms += now_ms() - t0; es_.h2d_bytes += n;
@@ -1109,6 +1120,57 @@ class CudaEngine : public Engine {
     float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
     es_.ingest_device_ms = ms;
     es_.ingest_bytes = static_cast<double>(n) + 4.0 * info->n_symbols + 12.0 * info->n_words;
+    return 0;
+  }
+
+  // pinned staging ring shared by all trainers of the process (cudaHostAlloc is slow, so it is done once)
+  static constexpr int STAGE_BUFS = 8;
+  static constexpr size_t STAGE_BYTES = 16u << 20;
+  struct StageRing { uint8_t* buf[STAGE_BUFS] = {}; std::mutex mu; };
+  static StageRing& stage_ring() { static StageRing r; return r; }
+
+  int stream_file(int fd, size_t n, uint8_t* d_text) {
+    StageRing& ring = stage_ring();
+    std::lock_guard<std::mutex> hold(ring.mu);  // one load at a time uses the ring
+    for (int b = 0; b < STAGE_BUFS; b++) if (!ring.buf[b]) CK(cudaHostAlloc(reinterpret_cast<void**>(&ring.buf[b]), STAGE_BYTES, cudaHostAllocDefault));
+    const size_t n_chunks = (n + STAGE_BYTES - 1) / STAGE_BYTES;
+    cudaEvent_t done[STAGE_BUFS];
+    for (int b = 0; b < STAGE_BUFS; b++) CK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    // state[b]: 0 = reader owns the buffer, 1 = filled (main may copy), 2 = copy issued (reader waits for the event)
+    std::atomic<int> state[STAGE_BUFS];
+    std::atomic<bool> failed{false};
+    for (int b = 0; b < STAGE_BUFS; b++) state[b].store(0);
+    std::vector<std::thread> readers;
+    for (int b = 0; b < STAGE_BUFS; b++) {
+      readers.emplace_back([&, b]() {
+        cudaSetDevice(dev_);
+        for (size_t c = b; c < n_chunks && !failed.load(); c += STAGE_BUFS) {
+          const size_t off = c * STAGE_BYTES, len = std::min(STAGE_BYTES, n - off);
+          size_t got = 0;
+          while (got < len) {
+            const ssize_t r = pread(fd, ring.buf[b] + got, len - got, static_cast<off_t>(off + got));
+            if (r <= 0) { failed.store(true); break; }
+            got += static_cast<size_t>(r);
+          }
+          state[b].store(1, std::memory_order_release);
+          while (state[b].load(std::memory_order_acquire) != 2 && !failed.load()) std::this_thread::yield();
+          if (failed.load()) break;
+          if (cudaEventSynchronize(done[b]) != cudaSuccess) { failed.store(true); break; }  // the buffer may be overwritten again
+          state[b].store(0, std::memory_order_release);
+        }
+      });
+    }
+    for (size_t c = 0; c < n_chunks && !failed.load(); c++) {  // issue the copies in file order
+      const int b = static_cast<int>(c % STAGE_BUFS);
+      const size_t off = c * STAGE_BYTES, len = std::min(STAGE_BYTES, n - off);
+      while (state[b].load(std::memory_order_acquire) != 1 && !failed.load()) std::this_thread::yield();
+      if (failed.load()) break;
+      if (cudaMemcpyAsync(d_text + off, ring.buf[b], len, cudaMemcpyHostToDevice, st_) != cudaSuccess || cudaEventRecord(done[b], st_) != cudaSuccess) { failed.store(true); break; }
+      state[b].store(2, std::memory_order_release);
+    }
+    for (auto& t : readers) t.join();
+    for (int b = 0; b < STAGE_BUFS; b++) cudaEventDestroy(done[b]);
+    if (failed.load()) { std::fprintf(stderr, "[ERROR]\t reading the corpus file failed\n"); return -1; }
     return 0;
   }
 

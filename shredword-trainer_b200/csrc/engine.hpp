@@ -60,6 +60,9 @@ class Engine {
   // A second load replaces the first.  Returns 0, -1 on failure, or 1 if the text contains NUL bytes (nothing is
   // loaded then: the caller blanks the spans the reference would not see and calls load again).
   virtual int load(const uint8_t* text, size_t n, const EngineConfig& cfg, LoadInfo* info) = 0;
+  // Same from an open file of n bytes (lets the engine pipeline the read with the host-to-device copy).  Returns like
+  // load(), or 2 if the engine has no file path (the caller maps the file and calls load()).
+  virtual int load_file(int /*fd*/, size_t /*n*/, const EngineConfig& /*cfg*/, LoadInfo* /*info*/) { return 2; }
   // Reset the pair table, count all adjacent non-unk pairs; *recs = PUSH records for entries with freq >= min.
   virtual int count_pairs(const Rec** recs, size_t* n) = 0;
   // Rewrite every leftmost non-overlapping (a,b) -> new_id, update the pair table, return the touched keys.

@@ -81,16 +81,23 @@ int TrainerCore::load_file(const char* path) {
   if (fd < 0) { std::fprintf(stderr, "[ERROR]\t Couldn't open file: %s\n", path); return -1; }  // bpe.cpp:118-122
   struct stat st;
   if (fstat(fd, &st) != 0) { ::close(fd); return -1; }
-  size_t n = static_cast<size_t>(st.st_size);
+  const size_t n = static_cast<size_t>(st.st_size);
   int rc;
   if (n == 0) {
     rc = load_buffer(reinterpret_cast<const uint8_t*>(""), 0);
   } else {
-    void* p = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
-    if (p == MAP_FAILED) { std::fprintf(stderr, "[ERROR]\t Couldn't map file: %s\n", path); ::close(fd); return -1; }
-    madvise(p, n, MADV_SEQUENTIAL);
-    rc = load_buffer(static_cast<const uint8_t*>(p), n);
-    munmap(p, n);
+    // fast path: the engine streams the file itself (pinned staging ring, read and PCIe copy overlapped)
+    const double t0 = now_ms();
+    EngineConfig ec = engine_config();
+    rc = eng_->load_file(fd, n, ec, &info_);
+    if (rc == 0) rc = finish_load(n, t0);
+    else if (rc > 0) {  // 1: NUL bytes (needs the host-side blanking pass), 2: engine without a file path -> map the file
+      void* p = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+      if (p == MAP_FAILED) { std::fprintf(stderr, "[ERROR]\t Couldn't map file: %s\n", path); ::close(fd); return -1; }
+      madvise(p, n, MADV_SEQUENTIAL);
+      rc = load_buffer(static_cast<const uint8_t*>(p), n);
+      munmap(p, n);
+    }
   }
   ::close(fd);
   return rc;
@@ -121,20 +128,30 @@ static std::vector<uint8_t> blank_hidden_spans(const uint8_t* text, size_t n) {
   return out;
 }
 
-int TrainerCore::load_buffer(const uint8_t* text, size_t n) {
-  double t0 = now_ms();
+EngineConfig TrainerCore::engine_config() const {
   EngineConfig ec;
   ec.unk_id = abi_->config.unk_id; ec.coverage = abi_->config.character_coverage; ec.min_freq = abi_->config.min_pair_freq;
   ec.vocab_size = abi_->config.target_vocab_size;
+  return ec;
+}
+
+int TrainerCore::load_buffer(const uint8_t* text, size_t n) {
+  double t0 = now_ms();
+  EngineConfig ec = engine_config();
   int rc = eng_->load(text, n, ec, &info_);
   if (rc == 1) {  // NUL bytes present
     std::vector<uint8_t> visible = blank_hidden_spans(text, n);
     rc = eng_->load(visible.data(), n, ec, &info_);
   }
   if (rc != 0) return -1;
+  return finish_load(n, t0);
+}
+
+// host mirrors of Corpus (bpe.h:37-41) after a successful engine load
+int TrainerCore::finish_load(size_t n, double t0) {
   corpus_bytes_ = n;
   loaded_ = true;
-  // host mirrors of Corpus (bpe.h:37-41): counts are real, words[] are non-NULL placeholders (symbols live in HBM)
+  // counts are real, words[] are non-NULL placeholders (the symbols live in HBM)
   std::free(abi_->corpus.words); std::free(abi_->corpus.word_counts);
   size_t N = info_.n_words;
   abi_->corpus.vocab_size = N;

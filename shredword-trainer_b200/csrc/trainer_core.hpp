@@ -34,6 +34,8 @@ class TrainerCore {
 
  private:
   void sync_mirrors();
+  EngineConfig engine_config() const;
+  int finish_load(size_t n_bytes, double t0_ms);
   bool is_phantom(int32_t a, int32_t b) const { return a == abi_->config.unk_id || b == abi_->config.unk_id; }
   void apply_records(const Rec* recs, size_t n);
 

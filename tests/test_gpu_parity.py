@@ -242,3 +242,24 @@ def test_two_trainers_interleaved(T):
     gb = [c for c in GOLDEN if c["name"] == "kat_py"][0]
     assert md5(_merge_bytes(a.merges())) == ga["merges_md5"] and md5(_merge_bytes(b.merges())) == gb["merges_md5"]
     a.destroy(); b.destroy()
+
+
+def test_load_corpus_from_file_paths(T, tmp_path):
+    """bpe_load_corpus(path) streams the file through the pinned staging ring; a file with NUL bytes falls back to the
+    host-side blanking pass; an empty file loads; sizes around the 32 MiB staging chunk are covered by a 70 MB file"""
+    blobs = {"nul": EDGE["nul_bytes"] + b"tail\x00gone", "empty": b"", "plain": EDGE["tabs_crlf"]}
+    for name, data in blobs.items():
+        p = tmp_path / (name + ".txt"); p.write_bytes(data)
+        o = Oracle(300, 0, 0.995, 1); o.load_corpus(str(p)); n = o.train()
+        t = T(300, 0, 0.995, 1); t.load_corpus(str(p))
+        assert t.num_words == o.num_words and t.train() == n and t.merges() == o.merges(), name
+        t.destroy(); o.destroy()
+    p = generated_corpus(str(tmp_path / "z70.txt"), 70_000_000, 5, 18, "zipf")
+    o = Oracle(600, 0, 0.995, 2000); o.load_corpus(p); n = o.train()
+    t = T(600, 0, 0.995, 2000); t.load_corpus(p)
+    t2 = T(600, 0, 0.995, 2000); t2.load_bytes(open(p, "rb").read())
+    assert t2.words()[:500] == t.words()[:500]   # streamed file == host buffer
+    assert t.num_words == o.num_words and t.train() == n and t.merges() == o.merges()
+    for x in (t, t2):
+        x.destroy()
+    o.destroy()

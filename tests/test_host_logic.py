@@ -90,3 +90,26 @@ def test_heap_array_identical_stepwise(case, hs):
         steps += 1
     assert _merges(t) == o.merges()
     hs.bpe_trainer_destroy(t); o.destroy()
+
+
+def test_load_from_file_nul_and_empty(hs, tmp_path):
+    """bpe_load_corpus(path): plain file, file with NUL bytes (the reference's fgets/strlen quirk, bpe.cpp:131-147), empty
+    file, missing file -- against the oracle, which replays the reference's line loop."""
+    hs.bpe_load_corpus.argtypes, hs.bpe_load_corpus.restype = [ctypes.POINTER(_Trainer), ctypes.c_char_p], ctypes.c_int
+    blobs = {"plain": b"abc abd abc\nxyz abc\n" * 40,
+             "nul": b"abc abd\x00hidden hidden hidden\nabc abd abc\x00\x00 zz\nplain line abc\n" * 9 + b"tail\x00gone",
+             "long_nul_line": (b"ab " * 3000) + b"\x00" + (b"zz " * 3000) + b"\nab ab zz\n",
+             "empty": b""}
+    for name, data in blobs.items():
+        p = tmp_path / (name + ".txt")
+        p.write_bytes(data)
+        o = Oracle(300, 0, 0.995, 1); o.load_corpus(str(p)); n = o.train()
+        t = hs.create_trainer(ctypes.byref(_Cfg(300, 0, 0.995, 1)))
+        assert hs.bpe_load_corpus(t, os.fsencode(str(p))) == 0
+        assert t.contents.n_words == o.num_words, name
+        assert hs.bpe_train(t) == n
+        assert _merges(t) == o.merges(), name
+        hs.bpe_trainer_destroy(t); o.destroy()
+    t = hs.create_trainer(ctypes.byref(_Cfg(300, 0, 0.995, 1)))
+    assert hs.bpe_load_corpus(t, os.fsencode(str(tmp_path / "missing.txt"))) == -1
+    hs.bpe_trainer_destroy(t)
