@@ -47,920 +47,12 @@
 namespace shred {
 namespace {
 
-#define CK(call)                                                                                              \
-  do {                                                                                                        \
-    cudaError_t e_ = (call);                                                                                  \
-    if (e_ != cudaSuccess) {                                                                                  \
-      std::fprintf(stderr, "[ERROR]\t CUDA: %s -> %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-      return -1;                                                                                              \
-    }                                                                                                         \
-  } while (0)
-
-#define RC(call)            \
-  do {                      \
-    int rc_ = (call);       \
-    if (rc_ != 0) return rc_; \
-  } while (0)
-
-typedef unsigned long long ull;
-
-constexpr int32_t DEAD = -1;
-constexpr uint32_t HDR_BIT = 0x80000000u;
-constexpr int32_t UNK_CODE_NEG = 0x7FFFFFFF;  // stored code of unk symbols when unk_id < 0
-constexpr uint64_t PT_EMPTY = ~0ull;
-constexpr uint64_t SEQ_MAX = ~0ull;
-constexpr int N_SM_FALLBACK = 148;
-
-enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32, ERR_BARRIER = 64,
-                  ERR_PEER_TIMEOUT = 128, ERR_INBOX_FULL = 256 };
-
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-  return x;
-}
-__device__ __forceinline__ bool is_delim(uint32_t c) { return c <= 32u && ((0x100002600ull >> c) & 1ull); }  // \t \n \r space
-__device__ __forceinline__ uint64_t fc_key(int32_t a, int32_t b) {  // bpe.cpp:277-278: both operands sign-extend
-  return (static_cast<uint64_t>(static_cast<int64_t>(a)) << 32) | static_cast<uint64_t>(static_cast<int64_t>(b));
-}
-
-struct Ctrl {  // mapped pinned host memory, written by finalize_block
-  volatile uint64_t flag;
-  uint64_t n_recs, occ, occ_local, pt_n, n_leaders, n_keys, cand_tiles;
-  uint32_t err, pad;
-};
-
-struct DevCounters {  // device memory
-  uint32_t wl_n, dt_n, rec_n, blocks_done;
-  ull occ;
-  ull pt_n;
-  uint32_t err, pad;
-  ull n_tokens;
-  uint32_t n_unique, blocks_done2;
-  uint32_t cand_tiles, bar;
-  uint32_t sent_ctas, pad4;
-};
-
-struct DeltaTable {
-  uint64_t* keys; ull* delta; ull* seq; uint32_t* list; uint64_t* klist;  // list/klist: slot and key of every used slot, dense
-  uint64_t mask; uint64_t empty; uint32_t cap;
-};
-struct PairEnt { uint64_t key; uint64_t freq; };  // one 16-byte load fetches both
-struct PairTable {
-  PairEnt* ent;
-  uint32_t* serial;  // dense id per entry = number of entries that existed when it was created (the host indexes by it)
-  uint64_t mask; uint64_t cap;
-};
-
-// ------------------------------------------------------------------------------------------------ hash-table helpers
-
-__device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, uint64_t key, int64_t delta, uint64_t seq) {
-  uint64_t slot = mix64(key) & dt.mask;
-  for (uint32_t probe = 0; probe < dt.cap; ++probe) {
-    uint64_t cur = dt.keys[slot];
-    if (cur == dt.empty) {
-      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot]), static_cast<ull>(dt.empty), static_cast<ull>(key));
-      if (prev == dt.empty) {
-        uint32_t idx = atomicAdd(&ctr->dt_n, 1u);
-        if (idx < dt.cap) { dt.list[idx] = static_cast<uint32_t>(slot); dt.klist[idx] = key; }
-        cur = key;
-      } else cur = prev;
-    }
-    if (cur == key) {
-      atomicAdd(&dt.delta[slot], static_cast<ull>(delta));
-      atomicMin(&dt.seq[slot], static_cast<ull>(seq));
-      return;
-    }
-    slot = (slot + 1) & dt.mask;
-  }
-  atomicOr(&ctr->err, ERR_DT_FULL);
-}
-
-__device__ __forceinline__ ull gtime() { ull t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ ulonglong2 ld_ent(const PairEnt* e) { return *reinterpret_cast<const ulonglong2*>(e); }
-
-// Finds `key` (inserting it if absent) and returns its slot; *old_freq = its frequency (0 for a new entry).
-// `first` is the already-loaded entry at the home slot (lets the caller issue several home loads back to back).
-// Only finalize_block calls this, with distinct keys per pass, so a claimed entry has exactly one writer.
-__device__ __forceinline__ uint64_t pt_find_or_insert(const PairTable& pt, DevCounters* ctr, uint64_t key, ulonglong2 first, uint64_t* old_freq) {
-  uint64_t slot = mix64(key) & pt.mask;
-  ulonglong2 e = first;
-  for (uint64_t probe = 0; probe < pt.cap; ++probe) {
-    if (e.x == key) { *old_freq = e.y; return slot; }
-    if (e.x == PT_EMPTY) {
-      const uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
-      if (prev == PT_EMPTY) { pt.serial[slot] = static_cast<uint32_t>(atomicAdd(&ctr->pt_n, 1ull)); *old_freq = 0; return slot; }
-      if (prev == key) { *old_freq = pt.ent[slot].freq; return slot; }
-    }
-    slot = (slot + 1) & pt.mask;
-    e = ld_ent(&pt.ent[slot]);
-  }
-  atomicOr(&ctr->err, ERR_PT_FULL);
-  *old_freq = 0;
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------------------ ingest
-
-struct WordTable {
-  ull* tag;       // 0 = empty
-  ull* first;     // smallest byte offset of an occurrence
-  ull* count;
-  uint32_t* len;
-  uint32_t* bucket;  // djb2 & 4095
-  uint64_t mask, cap;
-};
-
-// Each thread owns 16 consecutive corpus bytes (one uint4 load) and inserts every token that STARTS inside them.
-// text is padded with >= 32 spaces, so token walks terminate.
-__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
-  const uint64_t n16 = (n + 15) >> 4;
-  uint32_t my_tokens = 0;
-  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n16; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t base = t << 4;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t prev = base ? text[base - 1] : 32u;
-    // a NUL byte hides the rest of its line in the reference (fgets + strlen, bpe.cpp:131-147): report it, the host
-    // blanks the hidden spans and loads again
-    if (((v.x - 0x01010101u) & ~v.x & 0x80808080u) | ((v.y - 0x01010101u) & ~v.y & 0x80808080u) | ((v.z - 0x01010101u) & ~v.z & 0x80808080u) |
-        ((v.w - 0x01010101u) & ~v.w & 0x80808080u))
-      atomicOr(&ctr->err, ERR_HAS_NUL);
-    // delimiter mask of my 16 bytes
-    uint32_t dm = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) { uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 255u; dm |= (is_delim(c) ? 1u : 0u) << i; }
-    uint32_t starts = ~dm & ((dm << 1) | (is_delim(prev) ? 1u : 0u)) & 0xFFFFu;
-    while (starts) {
-      const int i = __ffs(starts) - 1;
-      starts &= starts - 1;
-      const uint64_t off = base + i;
-      if (off >= n) break;
-      // walk the token: two 32-bit multiplicative hashes (placement tag) + djb2 (reference bucket, hash.cpp:35-39)
-      uint32_t h1 = 2166136261u ^ seed, h2 = 0x9E3779B9u + seed, dj = 5381u, len = 0;
-      for (;;) {
-        const uint32_t c = text[off + len];
-        if (is_delim(c)) break;
-        h1 = (h1 ^ c) * 16777619u;
-        h2 = (h2 + c) * 0x85EBCA6Bu; h2 ^= h2 >> 15;
-        dj = dj * 33u + c;
-        ++len;
-      }
-      ++my_tokens;
-      const uint64_t tag = mix64((static_cast<uint64_t>(h1) << 32) | h2 | 0) | 1ull;
-      uint64_t slot = tag & wt.mask;
-      bool done = false;
-      for (uint32_t probe = 0; probe < 8192u && !done; ++probe) {
-        ull cur = wt.tag[slot];
-        if (cur == 0ull) {
-          ull prevt = atomicCAS(&wt.tag[slot], 0ull, static_cast<ull>(tag));
-          if (prevt == 0ull) {  // claimed: publish the immutable facts
-            wt.len[slot] = len;
-            wt.bucket[slot] = dj & 4095u;
-            atomicAdd(&ctr->n_unique, 1u);
-            cur = tag;
-          } else cur = prevt;
-        }
-        if (cur == tag) {
-          // first occurrence: most tokens come after the word's first sighting, so look before paying for an atomic
-          ull old = *reinterpret_cast<volatile ull*>(&wt.first[slot]);
-          if (off < old) old = atomicMin(&wt.first[slot], static_cast<ull>(off));
-          {  // count: lanes of this warp that hit the same slot right now add once (hot words are most of a Zipf corpus)
-            const unsigned am = __activemask();
-            const unsigned grp = __match_any_sync(am, slot);
-            if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(grp) - 1)) atomicAdd(&wt.count[slot], static_cast<ull>(__popc(grp)));
-          }
-          if (old != SEQ_MAX && old != off) {  // same tag: must be the same bytes, else retry ingest with a new seed
-            bool same = is_delim(text[old + len]);
-            for (uint32_t j = 0; j < len && same; j++) same = text[old + j] == text[off + j];
-            if (!same) atomicOr(&ctr->err, ERR_WT_COLLISION);
-          }
-          done = true;
-        } else slot = (slot + 1) & wt.mask;
-      }
-      if (!done) atomicOr(&ctr->err, ERR_WT_FULL);
-    }
-  }
-  // token count: warp reduce, one atomic per warp
-  for (int o = 16; o; o >>= 1) my_tokens += __shfl_down_sync(0xFFFFFFFFu, my_tokens, o);
-  if ((threadIdx.x & 31) == 0 && my_tokens) atomicAdd(&ctr->n_tokens, static_cast<ull>(my_tokens));
-}
-
-// unique slots -> dense list + per-bucket population
-__global__ void k_collect(WordTable wt, uint32_t* u_slot, uint32_t* u_n, uint32_t* bucket_cnt) {
-  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < wt.cap; s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    if (wt.tag[s] != 0ull) {
-      uint32_t idx = atomicAdd(u_n, 1u);
-      u_slot[idx] = static_cast<uint32_t>(s);
-      atomicAdd(&bucket_cnt[wt.bucket[s]], 1u);
-    }
-  }
-}
-
-// exclusive scan of 4096 bucket counts by one block of 1024 threads
-__global__ void k_scan4096(const uint32_t* cnt, uint32_t* start) {
-  __shared__ uint32_t part[1024];
-  const int t = threadIdx.x;
-  uint32_t c[4], s = 0;
-  for (int i = 0; i < 4; i++) { c[i] = cnt[t * 4 + i]; s += c[i]; }
-  part[t] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) { uint32_t v = t >= o ? part[t - o] : 0; __syncthreads(); part[t] += v; __syncthreads(); }
-  uint32_t run = part[t] - s;
-  for (int i = 0; i < 4; i++) { start[t * 4 + i] = run; run += c[i]; }
-  if (t == 1023) start[4096] = run;
-}
-
-__global__ void k_scatter(WordTable wt, const uint32_t* u_slot, uint32_t n, const uint32_t* bstart, uint32_t* cursor, uint32_t* tmp_slot, ull* tmp_first) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t s = u_slot[i], b = wt.bucket[s];
-    const uint32_t pos = bstart[b] + atomicAdd(&cursor[b], 1u);
-    tmp_slot[pos] = s;
-    tmp_first[pos] = wt.first[s];
-  }
-}
-
-// order of the words inside a djb2 bucket = first occurrence (all first offsets are distinct): wi = bucket_start + rank.
-// One CTA per bucket: bitonic sort of (first_offset << 24 | index) in shared memory.  Buckets larger than SORT_CAP
-// (more than ~30 M unique words) are left to k_rank_big.
-constexpr uint32_t SORT_CAP = 8192, SORT_THREADS = 512;
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_buckets(const uint32_t* __restrict__ tmp_slot, const ull* __restrict__ tmp_first, const uint32_t* __restrict__ bstart,
-                                                               uint32_t* __restrict__ order_slot) {
-  extern __shared__ ull sk[];
-  const uint32_t b = blockIdx.x, bs = bstart[b], n = bstart[b + 1] - bs;
-  if (n == 0 || n > SORT_CAP) return;
-  uint32_t np = 1;
-  while (np < n) np <<= 1;
-  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) sk[i] = i < n ? ((tmp_first[bs + i] << 24) | i) : ~0ull;
-  __syncthreads();
-  for (uint32_t k = 2; k <= np; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const ull a = sk[i], c = sk[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > c) == up) { sk[i] = c; sk[ixj] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order_slot[bs + i] = tmp_slot[bs + static_cast<uint32_t>(sk[i] & 0xFFFFFFull)];
-}
-
-// fallback for oversized buckets: each element counts the smaller first offsets in its bucket (O(n_b^2), L1 broadcast)
-__global__ void k_rank_big(WordTable wt, const uint32_t* tmp_slot, const ull* tmp_first, uint32_t n, const uint32_t* bstart, uint32_t* order_slot) {
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const uint32_t s = tmp_slot[e], b = wt.bucket[s];
-    const uint32_t bs = bstart[b], be = bstart[b + 1];
-    if (be - bs <= SORT_CAP) continue;
-    const ull mine = tmp_first[e];
-    uint32_t rank = 0;
-    for (uint32_t j = bs; j < be; j++) rank += tmp_first[j] < mine ? 1u : 0u;
-    order_slot[bs + rank] = s;
-  }
-}
-
-// unweighted byte histogram over unique words (histogram.cpp:30-36) + per-word facts in reference order
-__global__ void __launch_bounds__(256) k_hist_words(const uint8_t* __restrict__ text, WordTable wt, const uint32_t* order_slot, uint32_t n,
-                                                    ull* hist, ull* wcnt, uint32_t* wlen, ull* len1) {
-  __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
-  __syncthreads();
-  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
-    const uint32_t s = order_slot[wi];
-    const uint32_t len = wt.len[s];
-    const ull first = wt.first[s];
-    wcnt[wi] = wt.count[s];
-    wlen[wi] = len;
-    len1[wi] = static_cast<ull>(len) + 1ull;
-    for (uint32_t j = 0; j < len; j++) atomicAdd(&sh[text[first + j]], 1u);
-  }
-  __syncthreads();
-  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<ull>(sh[threadIdx.x]));
-}
-
-__global__ void __launch_bounds__(256) k_symbolize(const uint8_t* __restrict__ text, WordTable wt, const uint32_t* order_slot, uint32_t n,
-                                                   const ull* woff, const uint8_t* keep, int32_t unk_code, int32_t* ids, uint32_t* wid) {
-  __shared__ uint8_t sk[256];
-  sk[threadIdx.x] = keep[threadIdx.x];
-  __syncthreads();
-  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
-    const uint32_t s = order_slot[wi];
-    const uint32_t len = wt.len[s];
-    const ull first = wt.first[s];
-    const ull base = woff[wi];
-    ids[base] = static_cast<int32_t>(HDR_BIT | wi);
-    wid[base] = wi;
-    for (uint32_t j = 0; j < len; j++) { const uint32_t c = text[first + j]; ids[base + 1 + j] = sk[c] ? static_cast<int32_t>(c) : unk_code; wid[base + 1 + j] = wi; }
-  }
-}
-
-__global__ void k_fill_i32(int32_t* p, uint64_t from, uint64_t to, int32_t v) {
-  for (uint64_t i = from + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < to; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) p[i] = v;
-}
-__global__ void k_fill_u64(ull* p, uint64_t n, ull v) {
-  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) p[i] = v;
-}
-
-// ---- device-wide exclusive scan of uint64 (three passes; 2048 items per block) used at load and at compaction
-constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
-
-__device__ __forceinline__ ull block_excl_scan(ull v, ull* total) {  // 256 threads
-  __shared__ ull wsum[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  ull x = v;
-  for (int o = 1; o < 32; o <<= 1) { ull y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-  if (lane == 31) wsum[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    ull s = lane < 8 ? wsum[lane] : 0;
-    for (int o = 1; o < 8; o <<= 1) { ull y = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += y; }
-    if (lane < 8) wsum[lane] = s;
-  }
-  __syncthreads();
-  const ull before = warp ? wsum[warp - 1] : 0;
-  *total = wsum[7];
-  __syncthreads();
-  return before + x - v;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const ull* in, uint64_t n, ull* sums) {
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
-  ull s = 0;
-  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += in[base + i];
-  ull total;
-  block_excl_scan(s, &total);
-  if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(ull* sums, uint32_t nb, ull* grand_total) {  // one block
-  ull carry = 0;
-  for (uint32_t base = 0; base < nb; base += SCAN_THREADS) {
-    const uint32_t i = base + threadIdx.x;
-    ull v = i < nb ? sums[i] : 0, total;
-    ull ex = block_excl_scan(v, &total);
-    if (i < nb) sums[i] = carry + ex;
-    carry += total;
-  }
-  if (threadIdx.x == 0) *grand_total = carry;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const ull* in, uint64_t n, const ull* sums, ull* out) {
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
-  ull v[SCAN_ITEMS], s = 0;
-  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
-  ull total;
-  ull run = sums[blockIdx.x] + block_excl_scan(s, &total);
-  for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = run; run += v[i]; }
-}
-
-// -------------------------------------------------------------------------------------------------------------- count
-
-struct Params {
-  int32_t unk_id, unk_code;
-  uint64_t min_freq;
-};
-
-__device__ __forceinline__ int32_t code_to_id(int32_t code, const Params& P) { return (P.unk_id < 0 && code == P.unk_code) ? P.unk_id : code; }
-
-// bpe.cpp:197-214: every adjacent pair without unk adds the word's count; first sighting = flat position.
-// Flat, coalesced pass over the symbol array (int4 of ids + int4 of word indices per thread); the handful of distinct
-// pairs of a fresh corpus would serialise on global atomics, so each CTA first aggregates into a shared-memory hash
-// table (sum of counts, min position) and flushes one delta-table update per distinct pair at the end.
-constexpr uint32_t CNT_SLOTS = 2048, CNT_PROBES = 12;
-__device__ __forceinline__ void cnt_add(ull* s_key, ull* s_sum, ull* s_seq, const DeltaTable& dt, DevCounters* ctr, uint64_t key, uint64_t c, uint64_t seq) {
-  uint32_t slot = static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> 53) & (CNT_SLOTS - 1);
-  for (uint32_t probe = 0; probe < CNT_PROBES; ++probe) {
-    ull cur = s_key[slot];
-    if (cur == ~0ull) { const ull prev = atomicCAS(&s_key[slot], ~0ull, static_cast<ull>(key)); cur = prev == ~0ull ? key : prev; }
-    if (cur == key) {
-      atomicAdd(&s_sum[slot], static_cast<ull>(c));
-      if (seq < *reinterpret_cast<volatile ull*>(&s_seq[slot])) atomicMin(&s_seq[slot], static_cast<ull>(seq));  // positions grow along the grid-stride loop: rarely taken
-      return;
-    }
-    slot = (slot + 1) & (CNT_SLOTS - 1);
-  }
-  dt_add(dt, ctr, key, static_cast<int64_t>(c), seq);  // shared table crowded: straight to the global one
-}
-__global__ void __launch_bounds__(256) k_count(const int4* __restrict__ ids4, const uint4* __restrict__ wid4, uint32_t n4, const ull* __restrict__ wcnt, Params P,
-                                               DeltaTable dt, DevCounters* ctr, uint64_t seq_base) {
-  __shared__ ull s_key[CNT_SLOTS], s_sum[CNT_SLOTS], s_seq[CNT_SLOTS];
-  for (uint32_t i = threadIdx.x; i < CNT_SLOTS; i += blockDim.x) { s_key[i] = ~0ull; s_sum[i] = 0ull; s_seq[i] = SEQ_MAX; }
-  __syncthreads();
-  const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t n4_ceil = (n4 + 31u) & ~31u;  // whole warps stay in the loop so the shuffle below is full-width
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4_ceil; i += gridDim.x * blockDim.x) {
-    const bool in = i < n4;
-    const int4 v = in ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
-    int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-    if (lane == 31) nxt = (i + 1 < n4) ? __ldg(ids + 4 * (static_cast<uint64_t>(i) + 1)) : DEAD;
-    const int32_t s[5] = {v.x, v.y, v.z, v.w, nxt};
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) m |= (s[k] >= 0 && s[k + 1] >= 0 && s[k] != P.unk_code && s[k + 1] != P.unk_code) ? (1u << k) : 0u;
-    if (m) {
-      const uint4 w = __ldg(wid4 + i);
-      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++) if (m & (1u << k))
-        cnt_add(s_key, s_sum, s_seq, dt, ctr, fc_key(s[k], s[k + 1]), wcnt[ws[k]], seq_base | (4ull * i + k));
-    }
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < CNT_SLOTS; i += blockDim.x)
-    if (s_key[i] != ~0ull) dt_add(dt, ctr, s_key[i], static_cast<int64_t>(s_sum[i]), s_seq[i]);
-}
-
-// -------------------------------------------------------------------------------------------------------------- merge
-
-// ---- tile occurrence index ------------------------------------------------------------------------------------
-// planes[id * W + (t >> 5)] bit (t & 31) is set if token `id` occurs in slots [512 t, 512 t + 512] (the first slot of
-// the next tile included, so a pair that straddles the boundary is found from tile t).  Bits are only ever added between
-// two compactions, so the index is a superset of the truth: a merge scans exactly the tiles whose bit is set for both A
-// and B and provably misses nothing.  Late merges touch a few hundred of tens of thousands of tiles.
-constexpr uint32_t TILE_SHIFT = 9, TILE_SLOTS = 1u << TILE_SHIFT, TILE_I4 = TILE_SLOTS / 4, MAX_TILES_PER_CTA = 1024;
-static_assert(TILE_I4 % (32 * 4) == 0, "a tile is a whole number of warp chunks");
-
-__device__ __forceinline__ void plane_set(uint32_t* planes, uint32_t W, uint32_t id_cap, int32_t id, uint64_t slot) {
-  if (id < 0 || static_cast<uint32_t>(id) >= id_cap) return;
-  uint32_t t = static_cast<uint32_t>(slot >> TILE_SHIFT);
-  uint32_t* wp = planes + static_cast<uint64_t>(id) * W + (t >> 5);
-  uint32_t bit = 1u << (t & 31);
-  if (!(*wp & bit)) atomicOr(wp, bit);
-  if ((slot & (TILE_SLOTS - 1)) == 0 && t > 0) {
-    --t;
-    wp = planes + static_cast<uint64_t>(id) * W + (t >> 5);
-    bit = 1u << (t & 31);
-    if (!(*wp & bit)) atomicOr(wp, bit);
-  }
-}
-
-__global__ void __launch_bounds__(256) k_build_planes(const int32_t* __restrict__ ids, uint64_t n_slots, uint32_t* planes, uint32_t W, uint32_t id_cap) {
-  for (uint64_t p = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; p < n_slots; p += static_cast<uint64_t>(gridDim.x) * blockDim.x)
-    plane_set(planes, W, id_cap, ids[p], p);
-}
-
-// Shared by the count pass (COUNT=true, bpe.cpp:219-227) and the merge pass (bpe.cpp:297-318): fold the aggregated deltas
-// into the pair table and write one record per touched key for the host.  Runs in ONE block (any size): the stand-alone
-// k_finalize_count kernel, or the last block of k_scan_merge to finish.  Ends by publishing the counters to the host and
-// re-arming them.
-template <bool COUNT>
-__device__ __forceinline__ void finalize_block(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
-                                               int32_t A, int32_t B, const Params& P, uint64_t flag_value, ull* dbg = nullptr) {
-  __shared__ uint32_t s_rec_n;
-  if (dbg && threadIdx.x == 0) dbg[2] = gtime();
-  constexpr int ILP = 4;  // keys in flight per thread: the pass is a chain of dependent DRAM/L2 round trips
-  const uint32_t n = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
-  if (threadIdx.x == 0) s_rec_n = 0;
-  __syncthreads();
-  if (!COUNT && threadIdx.x == blockDim.x - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
-    const uint64_t k = fc_key(A, B);
-    uint64_t old;
-    const uint64_t s = pt_find_or_insert(pt, ctr, k, ld_ent(&pt.ent[mix64(k) & pt.mask]), &old);
-    pt.ent[s].freq = 0ull;
-  }
-  for (uint32_t base = 0; base < n; base += blockDim.x * ILP) {
-    uint64_t key[ILP]; uint32_t ds[ILP]; ulonglong2 home[ILP]; int64_t d[ILP]; uint64_t sq[ILP]; bool ok[ILP];
-#pragma unroll
-    for (int j = 0; j < ILP; j++) {
-      const uint32_t i = base + j * blockDim.x + threadIdx.x;
-      ok[j] = i < n;
-      if (ok[j]) { key[j] = dt.klist[i]; ds[j] = dt.list[i]; }
-    }
-#pragma unroll
-    for (int j = 0; j < ILP; j++) if (ok[j]) {
-      home[j] = ld_ent(&pt.ent[mix64(key[j]) & pt.mask]);
-      d[j] = static_cast<int64_t>(dt.delta[ds[j]]);
-      sq[j] = dt.seq[ds[j]];
-    }
-#pragma unroll
-    for (int j = 0; j < ILP; j++) if (ok[j]) {
-      dt.keys[ds[j]] = dt.empty; dt.delta[ds[j]] = 0ull; dt.seq[ds[j]] = SEQ_MAX;  // re-arm the scratch slot
-      const int32_t pa = static_cast<int32_t>(key[j] >> 32), pb = static_cast<int32_t>(key[j] & 0xFFFFFFFFu);  // bpe.cpp:301
-      Rec out; out.key = key[j]; out.seq = sq[j]; out.serial = REC_NO_SERIAL; out.kind = REC_PUSH; out.val = 0;
-      bool emit = false;
-      if (!COUNT && pa == A && pb == B) continue;  // bpe.cpp:302
-      if (!COUNT && (pa == P.unk_id || pb == P.unk_id)) {  // phantom pair: tracked by the host (Appendix A12)
-        out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d[j]); emit = true;
-      } else {
-        uint64_t old;
-        const uint64_t s = pt_find_or_insert(pt, ctr, key[j], home[j], &old);
-        uint64_t nf;
-        if (d[j] < 0) { const uint64_t ad = static_cast<uint64_t>(-d[j]); nf = old >= ad ? old - ad : 0; } else nf = old + static_cast<uint64_t>(d[j]);  // bpe.cpp:303-307
-        pt.ent[s].freq = nf;
-        if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
-        else if (!COUNT && old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
-        if (emit) out.serial = pt.serial[s];
-      }
-      if (emit) {
-        const uint32_t idx = atomicAdd(&s_rec_n, 1u);
-        if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
-      }
-    }
-  }
-  __syncthreads();
-  if (dbg && threadIdx.x == 0) dbg[3] = gtime();
-  if (threadIdx.x == 0) {  // counters for the host, then re-arm them for the next pass
-    ctrl->n_recs = s_rec_n < rec_cap ? s_rec_n : rec_cap;
-    ctrl->occ = ctr->occ;
-    ctrl->occ_local = ctr->occ;
-    ctrl->pt_n = ctr->pt_n;
-    ctrl->n_leaders = ctr->wl_n;
-    ctrl->n_keys = ctr->dt_n;
-    ctrl->cand_tiles = ctr->cand_tiles;
-    ctrl->err = ctr->err;
-    ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->occ = 0ull; ctr->cand_tiles = 0;
-  }
-  __threadfence_system();  // every thread's records (and thread 0's counters) are visible to the host ...
-  __syncthreads();
-  if (dbg && threadIdx.x == 0) dbg[4] = gtime();
-  if (threadIdx.x == 0) ctrl->flag = flag_value;  // ... before the flag it spins on
-}
-
-__global__ void __launch_bounds__(256) k_finalize_count(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
-                                                        uint64_t flag_value) {
-  finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
-}
-
-// One occurrence of (A,B) at flat position p: the four count deltas of bpe.cpp:274-290, computed independently per
-// occurrence.  Left neighbour = the id that stands there when the reference's left-to-right pass reaches p (N if the two
-// symbols before p were themselves merged in this pass), right neighbour = the raw id two slots on.
-__device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
-                                                int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
-                                                uint32_t& my_occ, uint64_t seq_base) {
-  const int32_t l1 = ids[p - 1];
-  const uint32_t wi = wid[p];  // independent loads first: wid -> wcnt is the longest chain
-  const int32_t r2 = ids[p + 2];
-  bool left_merged;
-  if (A != B) {
-    left_merged = l1 == B && ids[p - 2] == A;  // (A,B) pairs cannot overlap when A != B
-  } else {
-    uint64_t q = p;  // start of the run of A's: pairs are taken greedily from there (bpe.cpp:268-295)
-    while (ids[q - 1] == A) --q;
-    if ((p - q) & 1ull) return;  // second half of a merged pair, not an occurrence
-    left_merged = p > q;
-  }
-  const int64_t c = static_cast<int64_t>(wcnt[wi]);
-  const uint64_t seq = seq_base | (p * 4ull);
-  if (l1 >= 0) {
-    const int32_t lid = left_merged ? N : code_to_id(l1, P);
-    dt_add(dt, ctr, fc_key(lid, A), -c, seq + 0);
-    dt_add(dt, ctr, fc_key(lid, N), c, seq + 1);
-  }
-  if (r2 >= 0) {
-    const int32_t rid = code_to_id(r2, P);
-    dt_add(dt, ctr, fc_key(B, rid), -c, seq + 2);
-    dt_add(dt, ctr, fc_key(N, rid), c, seq + 3);
-  }
-  ml[atomicAdd(&ctr->wl_n, 1u)] = static_cast<uint32_t>(p);
-  ++my_occ;
-}
-
-// ---- multi-GPU exchange over NVLink peer memory ---------------------------------------------------------------
-// Every rank owns a contiguous range of the unique words and a full replica of the pair table and of the host heap.
-// Per pass (count, merge, token frequencies) each rank's aggregated (key, delta, sequence) list is the only thing that
-// crosses GPUs: the kernel STORES it straight into every peer's inbox (memory mapped with CUDA IPC, NVLink/NVSwitch),
-// raises a sequence flag there, waits for the peers' flags in its own inbox, and folds their entries into its own delta
-// table.  No host round trip and no NCCL call sits between the scan and the pair-table update.
-constexpr int MAX_RANKS = 8;
-constexpr uint64_t INBOX_ENTRIES = 1ull << 20, INBOX_HDR = 64, INBOX_BYTES = INBOX_HDR + INBOX_ENTRIES * 24;
-struct InboxHdr { ull seq; ull n; ull aux; };
-struct DistArgs {
-  int rank, world;
-  uint8_t* peer[MAX_RANKS];  // inbox base of every rank (peer[rank] is local memory)
-  ull xseq;                  // exchange number (>= 1); its parity selects the inbox half
-};
-__device__ __forceinline__ uint8_t* inbox_region(uint8_t* base, int world, ull xseq, int src) {
-  return base + ((xseq & 1ull) * static_cast<ull>(world) + static_cast<ull>(src)) * INBOX_BYTES;
-}
-
-// Software grid barrier for the cooperative per-merge kernel (all CTAs are co-resident: cudaLaunchCooperativeKernel).
-// `bar` only ever grows; `target` = value it reaches when every CTA of this launch has arrived at this barrier.
-__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uint32_t* err) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    const long long t0 = clock64();
-    while (static_cast<int32_t>(*reinterpret_cast<volatile uint32_t*>(bar) - target) < 0) {
-      if (clock64() - t0 > 4000000000ll) { atomicOr(err, ERR_BARRIER); break; }  // ~2 s: never hang the GPU on a host-side accounting bug
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// Cooperative exchange of the delta table's dense list (klist/list/delta/seq) between ranks.  Must be entered after a
-// grid barrier (the local list is complete); ends with one grid barrier (number `barrier_no` of this launch).
-// On return the local delta table holds the GLOBAL aggregate and *occ_global the global occurrence count.
-__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, uint32_t bar_base, int barrier_no, ull occ_local,
-                                                ull* occ_global) {
-  __shared__ bool last_sender;
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  const uint32_t n_local = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
-  if (n_local > INBOX_ENTRIES && gtid == 0) atomicOr(&ctr->err, ERR_INBOX_FULL);
-  const uint32_t n_send = n_local < INBOX_ENTRIES ? n_local : static_cast<uint32_t>(INBOX_ENTRIES);
-  for (uint32_t i = gtid; i < n_send; i += gthreads) {  // P2P stores into every peer's inbox
-    const uint32_t ds = dt.list[i];
-    const ull k = dt.klist[i], d = dt.delta[ds], sq = dt.seq[ds];
-    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
-      ull* e = reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR) + 3ull * i;
-      e[0] = k; e[1] = d; e[2] = sq;
-    }
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) last_sender = atomicAdd(&ctr->sent_ctas, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out: announce the list to the peers
-    __threadfence();
-    ctr->sent_ctas = 0;
-    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
-      InboxHdr* h = reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank));
-      h->n = n_send; h->aux = occ_local;
-    }
-    __threadfence_system();
-    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
-      *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
-  }
-  if (threadIdx.x == 0) {  // every CTA waits for the peers' lists to land in MY inbox (local memory)
-    const long long t0 = clock64();
-    for (int src = 0; src < D.world; src++) if (src != D.rank) {
-      volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
-      while (*f != D.xseq) {
-        __nanosleep(64);  // hundreds of CTAs poll this line while the peer's NVLink write has to get in
-        if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }  // ~4 s: never hang the GPU
-      }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  ull occ = occ_local;
-  for (int src = 0; src < D.world; src++) if (src != D.rank) {  // fold the peers' entries into my delta table
-    const uint8_t* reg = inbox_region(D.peer[D.rank], D.world, D.xseq, src);
-    const InboxHdr* h = reinterpret_cast<const InboxHdr*>(reg);
-    const ull n_src = __ldcv(&h->n);
-    occ += __ldcv(&h->aux);
-    const ull* e = reinterpret_cast<const ull*>(reg + INBOX_HDR);
-    for (ull i = gtid; i < n_src && i < INBOX_ENTRIES; i += gthreads)
-      dt_add(dt, ctr, __ldcv(e + 3 * i), static_cast<int64_t>(__ldcv(e + 3 * i + 1)), __ldcv(e + 3 * i + 2));
-  }
-  *occ_global = occ;
-  grid_barrier(&ctr->bar, bar_base + barrier_no * gridDim.x, &ctr->err);
-}
-
-// count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
-__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
-                                                             uint64_t flag_value, DistArgs D, uint32_t bar_base) {
-  ull occ;
-  exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
-  if (blockIdx.x == 0) finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
-}
-
-// token frequencies, sharded: sum of the ranks' partial arrays (T x uint64), same inbox protocol
-__global__ void __launch_bounds__(256) k_dist_sum_u64(ull* vals, uint64_t T, DevCounters* ctr, DistArgs D, uint32_t bar_base) {
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  for (uint64_t i = gtid; i < T; i += gthreads) {
-    const ull v = vals[i];
-    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
-      reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR)[i] = v;
-  }
-  __threadfence_system();
-  grid_barrier(&ctr->bar, bar_base + 1 * gridDim.x, &ctr->err);
-  if (gtid == 0) {
-    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
-      *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
-    const long long t0 = clock64();
-    for (int src = 0; src < D.world; src++) if (src != D.rank) {
-      volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
-      while (*f != D.xseq) if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }
-    }
-    __threadfence_system();
-  }
-  grid_barrier(&ctr->bar, bar_base + 2 * gridDim.x, &ctr->err);
-  for (uint64_t i = gtid; i < T; i += gthreads) {
-    ull v = vals[i];
-    for (int src = 0; src < D.world; src++) if (src != D.rank)
-      v += __ldcv(reinterpret_cast<const ull*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src) + INBOX_HDR) + i);
-    vals[i] = v;
-  }
-}
-
-// The per-merge kernel (cooperative launch, persistent grid = SM count x resident CTAs).
-//   phase 1  HBM-bound scan of the candidate tiles: every thread streams int4 (4 symbols) and tests the 4 adjacent pairs
-//            that start in it; an occurrence emits its count deltas straight into the delta table and is remembered
-//   barrier
-//   phase 2  every thread folds a share of the touched keys into the pair table and writes the records (bpe.cpp:297-318);
-//            the last CTA to finish publishes the counters and the flag the host spins on
-//   phase 3  in-place left-packed rewrite of the touched words (bpe.cpp:291-296), off the host's critical path: the
-//            first occurrence to claim a word (claimed[wi] = merge number) rewrites it; the last CTA re-arms the counters
-template <int UNROLL, bool DIST>
-__global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint32_t n_tiles, uint32_t tiles_per_cta,
-                                               const uint32_t* __restrict__ planeA, const uint32_t* __restrict__ planeB, uint32_t* planes, uint32_t W, uint32_t id_cap,
-                                               const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, const ull* __restrict__ woff, uint32_t* wlen,
-                                               uint32_t* claimed, uint32_t merge_no, int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt,
-                                               DevCounters* ctr, uint32_t* __restrict__ ml, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, uint64_t flag_value,
-                                               uint32_t bar_base, ull* dbg, DistArgs D) {
-  __shared__ uint32_t cand[MAX_TILES_PER_CTA];
-  __shared__ uint32_t n_cand;
-  __shared__ bool last;
-  int32_t* ids = reinterpret_cast<int32_t*>(ids4);
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  constexpr uint32_t CHUNK = 32u * UNROLL;
-  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[0] = gtime();
-  // ---- phase 1: this CTA's contiguous tile range -> candidate tiles (both tokens present); no planes = every tile
-  const uint32_t t0 = blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, n_tiles);
-  uint32_t my_occ = 0, nc_total = 0;
-  for (uint32_t ts = t0; ts < t1; ts += MAX_TILES_PER_CTA) {  // (one round unless the array exceeds ~900 M slots)
-  const uint32_t te_round = min(ts + MAX_TILES_PER_CTA, t1);
-  __syncthreads();
-  if (threadIdx.x == 0) n_cand = 0;
-  __syncthreads();
-  for (uint32_t t = ts + threadIdx.x; t < te_round; t += blockDim.x) {
-    const bool c = planeA == nullptr || (((planeA[t >> 5] & planeB[t >> 5]) >> (t & 31)) & 1u);
-    if (c) cand[atomicAdd(&n_cand, 1u)] = t;
-  }
-  __syncthreads();
-  const uint32_t nc = n_cand;
-  nc_total += nc;
-  for (uint32_t ci = warp; ci < nc; ci += warps) {
-    const uint64_t tb = static_cast<uint64_t>(cand[ci]) * TILE_I4;
-    const uint64_t te = min(tb + TILE_I4, static_cast<uint64_t>(n4));
-    for (uint64_t base = tb; base < te; base += CHUNK) {
-      int4 v[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        const uint64_t i = base + u * 32u + lane;
-        v[u] = i < n4 ? __ldcv(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
-      }
-      int32_t after = DEAD;  // first symbol after this chunk (needed by lane 31 of the last row)
-      if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldcv(ids + 4 * i); }
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
-        const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
-        if (lane == 31) nxt = row_next;
-        uint32_t m = 0;
-        m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
-        m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
-        m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
-        m |= (v[u].w == A && nxt == B) ? 8u : 0u;
-        if (__any_sync(0xFFFFFFFFu, m != 0)) {
-          const uint64_t p0 = (base + u * 32u + lane) * 4u;
-          while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull);
-          }
-        }
-      }
-    }
-  }
-  }
-  for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
-  if (lane == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
-  if (threadIdx.x == 0 && nc_total) atomicAdd(&ctr->cand_tiles, nc_total);
-  grid_barrier(&ctr->bar, bar_base + gridDim.x, &ctr->err);
-  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[1] = gtime();
-  const ull occ_local = ctr->occ;
-  ull occ_global = occ_local;
-  if (DIST) exchange_deltas(dt, ctr, D, bar_base, 2, occ_local, &occ_global);
-
-  // ---- phase 2: fold the aggregated deltas into the pair table, one key per thread
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  const uint32_t n_keys = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
-  if (gtid == gthreads - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
-    const uint64_t k = fc_key(A, B);
-    uint64_t old;
-    const uint64_t sl = pt_find_or_insert(pt, ctr, k, ld_ent(&pt.ent[mix64(k) & pt.mask]), &old);
-    pt.ent[sl].freq = 0ull;
-  }
-  bool wrote = false;
-  for (uint32_t i = gtid; i < n_keys; i += gthreads) {
-    const uint64_t key = dt.klist[i];
-    const uint32_t ds = dt.list[i];
-    const ulonglong2 home = ld_ent(&pt.ent[mix64(key) & pt.mask]);
-    const int64_t d = static_cast<int64_t>(dt.delta[ds]);
-    const uint64_t sq = dt.seq[ds];
-    dt.keys[ds] = dt.empty; dt.delta[ds] = 0ull; dt.seq[ds] = SEQ_MAX;  // re-arm the scratch slot
-    const int32_t pa = static_cast<int32_t>(key >> 32), pb = static_cast<int32_t>(key & 0xFFFFFFFFu);  // bpe.cpp:301
-    if (pa == A && pb == B) continue;  // bpe.cpp:302
-    Rec out; out.key = key; out.seq = sq; out.serial = REC_NO_SERIAL; out.kind = REC_PUSH; out.val = 0;
-    bool emit = false;
-    if (pa == P.unk_id || pb == P.unk_id) {  // phantom pair: tracked by the host (Appendix A12)
-      out.kind = REC_PHANTOM; out.val = static_cast<uint64_t>(d); emit = true;
-    } else {
-      uint64_t old;
-      const uint64_t sl = pt_find_or_insert(pt, ctr, key, home, &old);
-      uint64_t nf;
-      if (d < 0) { const uint64_t ad = static_cast<uint64_t>(-d); nf = old >= ad ? old - ad : 0; } else nf = old + static_cast<uint64_t>(d);  // bpe.cpp:303-307
-      pt.ent[sl].freq = nf;
-      if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
-      else if (old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
-      if (emit) out.serial = pt.serial[sl];
-    }
-    if (emit) {
-      const uint32_t idx = atomicAdd(&ctr->rec_n, 1u);
-      if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
-      wrote = true;
-    }
-  }
-  if (wrote) __threadfence_system();  // my records are visible to the host before I count myself done
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last && threadIdx.x == 0) {  // publish
-    __threadfence();
-    const uint32_t nr = *reinterpret_cast<volatile uint32_t*>(&ctr->rec_n);
-    ctrl->n_recs = nr < rec_cap ? nr : rec_cap;
-    ctrl->occ = occ_global;
-    ctrl->occ_local = occ_local;
-    ctrl->pt_n = *reinterpret_cast<volatile ull*>(&ctr->pt_n);
-    ctrl->n_leaders = *reinterpret_cast<volatile uint32_t*>(&ctr->wl_n);
-    ctrl->n_keys = n_keys;
-    ctrl->cand_tiles = *reinterpret_cast<volatile uint32_t*>(&ctr->cand_tiles);
-    ctrl->err = *reinterpret_cast<volatile uint32_t*>(&ctr->err);
-    __threadfence_system();
-    ctrl->flag = flag_value;
-    if (dbg) dbg[2] = gtime();
-  }
-
-  // ---- phase 3: rewrite the touched words in place (left-packed); the host is already replaying its heap
-  const uint32_t n_match = ctr->wl_n;
-  for (uint32_t i = gtid; i < n_match; i += gthreads) {
-    const uint32_t wi = wid[ml[i]];
-    if (atomicMax(&claimed[wi], merge_no) >= merge_no) continue;
-    const uint64_t q = woff[wi] + 1;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ids + q));        // the walk below is a chain of dependent loads:
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ids + q + 32));   // pull the word's lines into L1 first
-    uint64_t r = q, w = q;
-    int32_t cur = ids[r];
-    while (cur >= 0) {
-      const int32_t nxt = ids[r + 1];
-      if (cur == A && nxt == B) {
-        const int32_t nn = ids[r + 2];
-        ids[w] = N;
-        if (planes) plane_set(planes, W, id_cap, N, w);
-        ++w; r += 2;
-        cur = nn;
-      } else {
-        if (w != r) { ids[w] = cur; if (planes) plane_set(planes, W, id_cap, cur, w); }  // a moved symbol may enter another tile
-        ++w; ++r;
-        cur = nxt;
-      }
-    }
-    for (uint64_t k = w; k < r; k++) ids[k] = DEAD;
-    wlen[wi] = static_cast<uint32_t>(w - q);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(&ctr->blocks_done2, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last && threadIdx.x == 0) {  // every CTA has read the counters: re-arm them for the next merge
-    ctr->wl_n = 0; ctr->dt_n = 0; ctr->rec_n = 0; ctr->blocks_done = 0; ctr->blocks_done2 = 0; ctr->occ = 0ull; ctr->cand_tiles = 0;
-    if (dbg) dbg[3] = gtime();
-  }
-}
-
-__global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {
-  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < oldt.cap; s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const ulonglong2 e = ld_ent(&oldt.ent[s]);
-    if (e.x == PT_EMPTY) continue;
-    uint64_t slot = mix64(e.x) & newt.mask;
-    for (;;) {
-      uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&newt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(e.x));
-      if (prev == PT_EMPTY) { newt.ent[slot].freq = e.y; newt.serial[slot] = oldt.serial[s]; break; }
-      slot = (slot + 1) & newt.mask;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ compaction / save
-
-__global__ void k_rebase(const ull* in, uint32_t n, ull base, ull* out) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i] - base;
-}
-__global__ void k_len1(const uint32_t* wlen, uint32_t n, ull* len1) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) len1[i] = static_cast<ull>(wlen[i]) + 1ull;
-}
-__global__ void k_compact(const int32_t* __restrict__ src, const ull* __restrict__ old_off, const ull* __restrict__ new_off, const uint32_t* __restrict__ wlen,
-                          uint32_t n, int32_t* dst, uint32_t* dst_wid) {
-  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
-    const ull so = old_off[wi], d = new_off[wi];
-    const uint32_t len = wlen[wi];
-    for (uint32_t j = 0; j <= len; j++) { dst[d + j] = src[so + j]; dst_wid[d + j] = wi; }
-  }
-}
-__global__ void k_token_freq(const int32_t* __restrict__ ids, const ull* __restrict__ woff, const uint32_t* __restrict__ wlen, const ull* __restrict__ wcnt,
-                             uint32_t n, Params P, ull* freq, uint64_t T) {
-  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n; wi += gridDim.x * blockDim.x) {
-    const ull base = woff[wi] + 1, c = wcnt[wi];
-    const uint32_t len = wlen[wi];
-    for (uint32_t j = 0; j < len; j++) {
-      const int32_t id = code_to_id(ids[base + j], P);
-      if (id >= 0 && static_cast<uint64_t>(id) < T) atomicAdd(&freq[id], c);  // bpe.cpp:413
-    }
-  }
-}
+#include "common.cuh"
+#include "kernels_ingest.cuh"
+#include "kernels_count.cuh"
+#include "kernels_fold.cuh"
+#include "kernels_dist.cuh"
+#include "kernels_merge.cuh"
 
 // ============================================================================================================ engine
 

@@ -1,0 +1,133 @@
+// kernels_dist.cuh -- multi-GPU: inbox protocol over NVLink peer memory, grid barrier, delta exchange, sharded count/sum kernels.
+// Fragment of engine_cuda.cu: included inside `namespace shred { namespace {`, in the order listed there.
+#pragma once
+
+// ---- multi-GPU exchange over NVLink peer memory ---------------------------------------------------------------
+// Every rank owns a contiguous range of the unique words and a full replica of the pair table and of the host heap.
+// Per pass (count, merge, token frequencies) each rank's aggregated (key, delta, sequence) list is the only thing that
+// crosses GPUs: the kernel STORES it straight into every peer's inbox (memory mapped with CUDA IPC, NVLink/NVSwitch),
+// raises a sequence flag there, waits for the peers' flags in its own inbox, and folds their entries into its own delta
+// table.  No host round trip and no NCCL call sits between the scan and the pair-table update.
+constexpr int MAX_RANKS = 8;
+constexpr uint64_t INBOX_ENTRIES = 1ull << 20, INBOX_HDR = 64, INBOX_BYTES = INBOX_HDR + INBOX_ENTRIES * 24;
+struct InboxHdr { ull seq; ull n; ull aux; };
+struct DistArgs {
+  int rank, world;
+  uint8_t* peer[MAX_RANKS];  // inbox base of every rank (peer[rank] is local memory)
+  ull xseq;                  // exchange number (>= 1); its parity selects the inbox half
+};
+__device__ __forceinline__ uint8_t* inbox_region(uint8_t* base, int world, ull xseq, int src) {
+  return base + ((xseq & 1ull) * static_cast<ull>(world) + static_cast<ull>(src)) * INBOX_BYTES;
+}
+
+// Software grid barrier for the cooperative per-merge kernel (all CTAs are co-resident: cudaLaunchCooperativeKernel).
+// `bar` only ever grows; `target` = value it reaches when every CTA of this launch has arrived at this barrier.
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uint32_t* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(*reinterpret_cast<volatile uint32_t*>(bar) - target) < 0) {
+      if (clock64() - t0 > 4000000000ll) { atomicOr(err, ERR_BARRIER); break; }  // ~2 s: never hang the GPU on a host-side accounting bug
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Cooperative exchange of the delta table's dense list (klist/list/delta/seq) between ranks.  Must be entered after a
+// grid barrier (the local list is complete); ends with one grid barrier (number `barrier_no` of this launch).
+// On return the local delta table holds the GLOBAL aggregate and *occ_global the global occurrence count.
+__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, uint32_t bar_base, int barrier_no, ull occ_local,
+                                                ull* occ_global) {
+  __shared__ bool last_sender;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t n_local = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
+  if (n_local > INBOX_ENTRIES && gtid == 0) atomicOr(&ctr->err, ERR_INBOX_FULL);
+  const uint32_t n_send = n_local < INBOX_ENTRIES ? n_local : static_cast<uint32_t>(INBOX_ENTRIES);
+  for (uint32_t i = gtid; i < n_send; i += gthreads) {  // P2P stores into every peer's inbox
+    const uint32_t ds = dt.list[i];
+    const ull k = dt.klist[i], d = dt.delta[ds], sq = dt.seq[ds];
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
+      ull* e = reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR) + 3ull * i;
+      e[0] = k; e[1] = d; e[2] = sq;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last_sender = atomicAdd(&ctr->sent_ctas, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out: announce the list to the peers
+    __threadfence();
+    ctr->sent_ctas = 0;
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
+      InboxHdr* h = reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank));
+      h->n = n_send; h->aux = occ_local;
+    }
+    __threadfence_system();
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
+      *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
+  }
+  if (threadIdx.x == 0) {  // every CTA waits for the peers' lists to land in MY inbox (local memory)
+    const long long t0 = clock64();
+    for (int src = 0; src < D.world; src++) if (src != D.rank) {
+      volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
+      while (*f != D.xseq) {
+        __nanosleep(64);  // hundreds of CTAs poll this line while the peer's NVLink write has to get in
+        if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }  // ~4 s: never hang the GPU
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  ull occ = occ_local;
+  for (int src = 0; src < D.world; src++) if (src != D.rank) {  // fold the peers' entries into my delta table
+    const uint8_t* reg = inbox_region(D.peer[D.rank], D.world, D.xseq, src);
+    const InboxHdr* h = reinterpret_cast<const InboxHdr*>(reg);
+    const ull n_src = __ldcv(&h->n);
+    occ += __ldcv(&h->aux);
+    const ull* e = reinterpret_cast<const ull*>(reg + INBOX_HDR);
+    for (ull i = gtid; i < n_src && i < INBOX_ENTRIES; i += gthreads)
+      dt_add(dt, ctr, __ldcv(e + 3 * i), static_cast<int64_t>(__ldcv(e + 3 * i + 1)), __ldcv(e + 3 * i + 2));
+  }
+  *occ_global = occ;
+  grid_barrier(&ctr->bar, bar_base + barrier_no * gridDim.x, &ctr->err);
+}
+
+// count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
+__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
+                                                             uint64_t flag_value, DistArgs D, uint32_t bar_base) {
+  ull occ;
+  exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
+  if (blockIdx.x == 0) finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
+}
+
+// token frequencies, sharded: sum of the ranks' partial arrays (T x uint64), same inbox protocol
+__global__ void __launch_bounds__(256) k_dist_sum_u64(ull* vals, uint64_t T, DevCounters* ctr, DistArgs D, uint32_t bar_base) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  for (uint64_t i = gtid; i < T; i += gthreads) {
+    const ull v = vals[i];
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
+      reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR)[i] = v;
+  }
+  __threadfence_system();
+  grid_barrier(&ctr->bar, bar_base + 1 * gridDim.x, &ctr->err);
+  if (gtid == 0) {
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
+      *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
+    const long long t0 = clock64();
+    for (int src = 0; src < D.world; src++) if (src != D.rank) {
+      volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
+      while (*f != D.xseq) if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_PEER_TIMEOUT); break; }
+    }
+    __threadfence_system();
+  }
+  grid_barrier(&ctr->bar, bar_base + 2 * gridDim.x, &ctr->err);
+  for (uint64_t i = gtid; i < T; i += gthreads) {
+    ull v = vals[i];
+    for (int src = 0; src < D.world; src++) if (src != D.rank)
+      v += __ldcv(reinterpret_cast<const ull*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src) + INBOX_HDR) + i);
+    vals[i] = v;
+  }
+}

@@ -263,3 +263,29 @@ def test_load_corpus_from_file_paths(T, tmp_path):
     for x in (t, t2):
         x.destroy()
     o.destroy()
+
+
+MIDSIZE = [
+    ("zipf30m_unk-1", (30_000_000, 21, 18, "zipf"), (3000, -1, 0.9995, 50)),
+    ("multi20m_unk-5", (20_000_000, 22, 17, "multi"), (5000, -5, 0.9, 5)),
+    ("multi20m_unk65", (20_000_000, 23, 17, "multi"), (4000, 65, 0.5, 20)),
+    ("zipf50m_unk300", (50_000_000, 24, 20, "zipf"), (6000, 300, 0.995, 100)),
+]
+
+
+@pytest.mark.parametrize("name,gen,cfg", MIDSIZE, ids=[m[0] for m in MIDSIZE])
+def test_midsize_configs_match_oracle(name, gen, cfg, T, tmp_path):
+    """20-50 MB corpora x the awkward configurations (negative unk ids, unk colliding with a byte / a future merge id,
+    low coverage, low min_pair_freq): merge list and vocab file against the oracle"""
+    p = generated_corpus(str(tmp_path / "c.txt"), *gen)
+    o = Oracle(*cfg); o.load_corpus(p); n = o.train()
+    t = T(*cfg); t.load_corpus(p)
+    assert t.num_words == o.num_words
+    assert t.train() == n
+    assert t.merges() == o.merges()
+    mo, vo, mg, vg = (str(tmp_path / x) for x in ("mo", "vo", "mg", "vg"))
+    o.save(mo, vo); t.save(mg, vg)
+    assert open(mo, "rb").read() == open(mg, "rb").read()
+    if cfg[1] < 0 or cfg[1] < 256 + n:
+        assert open(vo, "rb").read() == open(vg, "rb").read()
+    t.destroy(); o.destroy()
