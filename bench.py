@@ -314,7 +314,7 @@ def main():
                    "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
                    "ingest_device_ms": st["ingest_device_ms"], "ingest_gbs": st["ingest_bytes"] / (st["ingest_device_ms"] * 1e-3) / 1e9 if st["ingest_device_ms"] else None,
                    "count_device_ms": st["count_device_ms"], "count_gbs": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 if st["count_device_ms"] else None,
-                   "h2d_ms": st["h2d_ms"], "load_corpus_from_file_s": load_file_s, "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
+                   "h2d_ms": st["h2d_ms"], "load_corpus_from_file_s": load_file_s, "load_s_steps": [round(x[1], 4) for x in steps], "train_s_steps": [round(x[2], 4) for x in steps], "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
     }
     if replicas:

@@ -215,6 +215,31 @@ class CudaEngine : public Engine {
     return 0;
   }
 
+  // The tile index is the one GB-sized buffer whose size is close to the corpus text's: handing it back to the stream-ordered
+  // pool lets the pool give it to the next trainer's text buffer and then grow again for the next index (a ~1 s stall when
+  // it happens).  One spare per process is parked here instead.
+  struct PlaneCache { uint32_t* ptr = nullptr; uint64_t bytes = 0; int dev = -1; std::mutex mu; };
+  static PlaneCache& plane_cache() { static PlaneCache c; return c; }
+  int acquire_planes(uint64_t bytes) {
+    PlaneCache& c = plane_cache();
+    {
+      std::lock_guard<std::mutex> hold(c.mu);
+      if (c.ptr && c.dev == dev_ && c.bytes >= bytes && c.bytes <= bytes + bytes / 2) { planes_ = c.ptr; planes_bytes_ = c.bytes; c.ptr = nullptr; c.bytes = 0; return 0; }
+    }
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&planes_), bytes, st_));
+    planes_bytes_ = bytes;
+    return 0;
+  }
+  void release_planes() {
+    if (!planes_) return;
+    cudaStreamSynchronize(st_);  // nothing queued may still touch it
+    PlaneCache& c = plane_cache();
+    std::lock_guard<std::mutex> hold(c.mu);
+    if (!c.ptr) { c.ptr = planes_; c.bytes = planes_bytes_; c.dev = dev_; }
+    else cudaFreeAsync(planes_, st_);
+    planes_ = nullptr; planes_bytes_ = 0;
+  }
+
   // pinned staging ring shared by all trainers of the process (cudaHostAlloc is slow, so it is done once)
   static constexpr int STAGE_BUFS = 8;
   static constexpr size_t STAGE_BYTES = 16u << 20;
@@ -402,19 +427,40 @@ class CudaEngine : public Engine {
   // (re)build the tile occurrence index for the current ids buffer
   int build_planes() {
     if (std::getenv("SHRED_NO_TILE_INDEX")) return 0;
-    const uint32_t n_tiles_cap = static_cast<uint32_t>((ids_cap_ + TILE_SLOTS - 1) >> TILE_SHIFT);
-    const uint32_t W = (n_tiles_cap + 31) / 32;
+    const double tb0 = now_ms();
     const uint32_t id_cap = static_cast<uint32_t>(256 + vocab_hint_ + 64);
-    const uint64_t bytes = static_cast<uint64_t>(id_cap) * W * 4;
-    if (!planes_ || W != plane_words_ || id_cap != id_cap_) {
-      if (planes_) { cudaFreeAsync(planes_, st_); planes_ = nullptr; }
-      size_t free_b = 0, total_b = 0;
-      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 3) { plane_words_ = 0; id_cap_ = 0; return 0; }  // too big: scan every tile
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&planes_), bytes, st_));
-      plane_words_ = W; id_cap_ = id_cap;
+    // finest tiling whose bit planes fit the budget (a tile is at least one warp row = 128 slots)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    uint64_t budget = 6ull << 30;
+    if (const char* e = std::getenv("SHRED_TILE_INDEX_MB")) budget = static_cast<uint64_t>(std::atoll(e)) << 20;
+    if (budget > (free_b + (planes_ ? static_cast<uint64_t>(id_cap_) * plane_words_ * 4 : 0)) / 3) budget = (free_b + (planes_ ? static_cast<uint64_t>(id_cap_) * plane_words_ * 4 : 0)) / 3;
+    uint32_t shift = MIN_TILE_SHIFT, W = 0;
+    uint64_t bytes = 0;
+    for (;; ++shift) {
+      const uint32_t n_tiles_cap = static_cast<uint32_t>((ids_cap_ + (1ull << shift) - 1) >> shift);
+      W = (n_tiles_cap + 31) / 32;
+      bytes = static_cast<uint64_t>(id_cap) * W * 4;
+      if (bytes <= budget || shift == MAX_TILE_SHIFT) break;
+    }
+    if (bytes > budget) {  // even the coarsest tiling is too big: scan every tile
+      release_planes();
+      plane_words_ = 0; id_cap_ = 0; tile_shift_ = MAX_TILE_SHIFT;
+      return 0;
+    }
+    if (!planes_ || W != plane_words_ || id_cap != id_cap_ || shift != tile_shift_) {
+      release_planes();
+      RC(acquire_planes(bytes));
+      plane_words_ = W; id_cap_ = id_cap; tile_shift_ = shift;
     }
     CK(cudaMemsetAsync(planes_, 0, bytes, st_));
-    if (n_slots_) { k_build_planes<<<grid_for(n_slots_, 256), 256, 0, st_>>>(ids_[cur_], n_slots_, planes_, plane_words_, id_cap_); launches_++; }
+    const double tb1 = now_ms();
+    if (n_slots_) { k_build_planes<<<grid_for(n_slots_, 256), 256, 0, st_>>>(ids_[cur_], n_slots_, planes_, plane_words_, id_cap_, tile_shift_); launches_++; }
+    if (dbg_print_) {
+      cudaStreamSynchronize(st_);
+      std::fprintf(stderr, "[PLANES]\t shift %u, %.1f MB: alloc+memset issue %.2f ms, build %.2f ms (free %.1f GB)\n", tile_shift_, bytes / 1048576.0, tb1 - tb0, now_ms() - tb1,
+                   free_b / 1073741824.0);
+    }
     return 0;
   }
 
@@ -536,7 +582,7 @@ class CudaEngine : public Engine {
     if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
     ull* a_dbg = timed ? dbg_ : nullptr;
-    const uint32_t n_tiles = static_cast<uint32_t>((n_slots_ + TILE_SLOTS - 1) >> TILE_SHIFT);
+    const uint32_t n_tiles = static_cast<uint32_t>((n_slots_ + (1ull << tile_shift_) - 1) >> tile_shift_);
     int grid = detect_grid(n4);
     const uint32_t tiles_per_cta = (n_tiles + grid - 1) / grid;
     const bool indexed = planes_ && static_cast<uint32_t>(a) < id_cap_ && static_cast<uint32_t>(b) < id_cap_;
@@ -544,7 +590,7 @@ class CudaEngine : public Engine {
     const uint32_t* pb = indexed ? planes_ + static_cast<uint64_t>(b) * plane_words_ : nullptr;
     {
       int4* a_ids = reinterpret_cast<int4*>(ids_[cur_]);
-      uint32_t a_n4 = n4, a_nt = n_tiles, a_tpc = tiles_per_cta, a_W = plane_words_, a_idcap = id_cap_, a_mno = merge_no_, a_reccap = rec_cap_;
+      uint32_t a_n4 = n4, a_nt = n_tiles, a_tpc = tiles_per_cta, a_ts = tile_shift_, a_W = plane_words_, a_idcap = id_cap_, a_mno = merge_no_, a_reccap = rec_cap_;
       const uint32_t* a_wid = wid_[cur_]; const ull* a_wcnt = wcnt_; const ull* a_woff = woff_[cur_];
       int32_t a_A = a, a_B = b, a_N = new_id;
       Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
@@ -553,7 +599,7 @@ class CudaEngine : public Engine {
       DistArgs a_D = dist_;
       if (world_ > 1) a_D = next_exchange();
       bar_count_ += (world_ > 1 ? 2u : 1u) * static_cast<uint32_t>(grid);
-      void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
+      void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &a_ts, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
                       &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &a_dbg, &a_D};
       const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<4, true>) : reinterpret_cast<const void*>(k_merge<4, false>);
       if (plain_launch_) CK(cudaLaunchKernel(kfn, dim3(grid), dim3(256), args, 0, st_));  // experiment: same grid, no co-residency check by the driver
@@ -568,7 +614,7 @@ class CudaEngine : public Engine {
       float ms = 0;
       CK(cudaEventSynchronize(ev1_));
       cudaEventElapsedTime(&ms, ev0_, ev1_);
-      const double algo = 4.0 * static_cast<double>(n4) * 4.0, touched = 4.0 * TILE_SLOTS * static_cast<double>(ctrl_->cand_tiles);
+      const double algo = 4.0 * static_cast<double>(n4) * 4.0, touched = 4.0 * static_cast<double>(1u << tile_shift_) * static_cast<double>(ctrl_->cand_tiles);
       es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += algo; es_.scan_bytes_touched += touched;
       const double p1 = (dbg_[1] - dbg_[0]) * 1e-6, p2 = (dbg_[2] - dbg_[1]) * 1e-6, p3 = (dbg_[3] - dbg_[2]) * 1e-6;  // ms: scan+emit+barrier | fold+publish | rewrite
       es_.scan_phase_ms += p1;
@@ -737,7 +783,7 @@ class CudaEngine : public Engine {
     if (wl_) cudaFreeAsync(wl_, st_); wl_ = nullptr;
     for (int i = 0; i < 2; i++) { if (wid_[i]) cudaFreeAsync(wid_[i], st_); wid_[i] = nullptr; }
     if (claimed_) cudaFreeAsync(claimed_, st_); claimed_ = nullptr;
-    if (planes_) cudaFreeAsync(planes_, st_); planes_ = nullptr; plane_words_ = 0; id_cap_ = 0;
+    release_planes(); plane_words_ = 0; id_cap_ = 0; tile_shift_ = 9;
     n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
   }
   void release_all() {
@@ -781,7 +827,8 @@ class CudaEngine : public Engine {
   std::vector<uint64_t> host_counts_;
   std::string rdv_prefix_;
   uint32_t* planes_ = nullptr;
-  uint32_t plane_words_ = 0, id_cap_ = 0;
+  uint64_t planes_bytes_ = 0;
+  uint32_t plane_words_ = 0, id_cap_ = 0, tile_shift_ = 9;
   uint64_t cand_tiles_total_ = 0, tiles_total_ = 0;
   DeltaTable dt_{};
   PairTable pt_{};

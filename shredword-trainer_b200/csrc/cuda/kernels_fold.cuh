@@ -5,20 +5,21 @@
 // -------------------------------------------------------------------------------------------------------------- merge
 
 // ---- tile occurrence index ------------------------------------------------------------------------------------
-// planes[id * W + (t >> 5)] bit (t & 31) is set if token `id` occurs in slots [512 t, 512 t + 512] (the first slot of
+// planes[id * W + (t >> 5)] bit (t & 31) is set if token `id` occurs in slots [T t, T t + T] with T = 2^tile_shift (the first slot of
 // the next tile included, so a pair that straddles the boundary is found from tile t).  Bits are only ever added between
 // two compactions, so the index is a superset of the truth: a merge scans exactly the tiles whose bit is set for both A
 // and B and provably misses nothing.  Late merges touch a few hundred of tens of thousands of tiles.
-constexpr uint32_t TILE_SHIFT = 9, TILE_SLOTS = 1u << TILE_SHIFT, TILE_I4 = TILE_SLOTS / 4, MAX_TILES_PER_CTA = 1024;
-static_assert(TILE_I4 % (32 * 4) == 0, "a tile is a whole number of warp chunks");
+// The tile size is chosen per corpus (2^tile_shift slots, 128 ... 4096): the finest tiling whose planes stay within a
+// few GB, because finer tiles mean fewer bytes scanned per merge.
+constexpr uint32_t MIN_TILE_SHIFT = 7, MAX_TILE_SHIFT = 12, MAX_TILES_PER_CTA = 1024;
 
-__device__ __forceinline__ void plane_set(uint32_t* planes, uint32_t W, uint32_t id_cap, int32_t id, uint64_t slot) {
+__device__ __forceinline__ void plane_set(uint32_t* planes, uint32_t W, uint32_t id_cap, uint32_t tile_shift, int32_t id, uint64_t slot) {
   if (id < 0 || static_cast<uint32_t>(id) >= id_cap) return;
-  uint32_t t = static_cast<uint32_t>(slot >> TILE_SHIFT);
+  uint32_t t = static_cast<uint32_t>(slot >> tile_shift);
   uint32_t* wp = planes + static_cast<uint64_t>(id) * W + (t >> 5);
   uint32_t bit = 1u << (t & 31);
   if (!(*wp & bit)) atomicOr(wp, bit);
-  if ((slot & (TILE_SLOTS - 1)) == 0 && t > 0) {
+  if ((slot & ((1ull << tile_shift) - 1)) == 0 && t > 0) {
     --t;
     wp = planes + static_cast<uint64_t>(id) * W + (t >> 5);
     bit = 1u << (t & 31);
@@ -26,9 +27,10 @@ __device__ __forceinline__ void plane_set(uint32_t* planes, uint32_t W, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(256) k_build_planes(const int32_t* __restrict__ ids, uint64_t n_slots, uint32_t* planes, uint32_t W, uint32_t id_cap) {
+__global__ void __launch_bounds__(256) k_build_planes(const int32_t* __restrict__ ids, uint64_t n_slots, uint32_t* planes, uint32_t W, uint32_t id_cap,
+                                                      uint32_t tile_shift) {
   for (uint64_t p = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; p < n_slots; p += static_cast<uint64_t>(gridDim.x) * blockDim.x)
-    plane_set(planes, W, id_cap, ids[p], p);
+    plane_set(planes, W, id_cap, tile_shift, ids[p], p);
 }
 
 // Shared by the count pass (COUNT=true, bpe.cpp:219-227) and the merge pass (bpe.cpp:297-318): fold the aggregated deltas

@@ -11,7 +11,7 @@
 //   phase 3  in-place left-packed rewrite of the touched words (bpe.cpp:291-296), off the host's critical path: the
 //            first occurrence to claim a word (claimed[wi] = merge number) rewrites it; the last CTA re-arms the counters
 template <int UNROLL, bool DIST>
-__global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint32_t n_tiles, uint32_t tiles_per_cta,
+__global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint32_t n_tiles, uint32_t tiles_per_cta, uint32_t tile_shift,
                                                const uint32_t* __restrict__ planeA, const uint32_t* __restrict__ planeB, uint32_t* planes, uint32_t W, uint32_t id_cap,
                                                const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, const ull* __restrict__ woff, uint32_t* wlen,
                                                uint32_t* claimed, uint32_t merge_no, int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt,
@@ -22,7 +22,6 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
   __shared__ bool last;
   int32_t* ids = reinterpret_cast<int32_t*>(ids4);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  constexpr uint32_t CHUNK = 32u * UNROLL;
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[0] = gtime();
   // ---- phase 1: this CTA's contiguous tile range -> candidate tiles (both tokens present); no planes = every tile
   const uint32_t t0 = blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, n_tiles);
@@ -39,35 +38,40 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
   __syncthreads();
   const uint32_t nc = n_cand;
   nc_total += nc;
-  for (uint32_t ci = warp; ci < nc; ci += warps) {
-    const uint64_t tb = static_cast<uint64_t>(cand[ci]) * TILE_I4;
-    const uint64_t te = min(tb + TILE_I4, static_cast<uint64_t>(n4));
-    for (uint64_t base = tb; base < te; base += CHUNK) {
-      int4 v[UNROLL];
+  // the candidate tiles as one flat list of rows (a row = 32 lanes x int4 = 128 slots = 512 B); every warp keeps UNROLL rows,
+  // possibly of different tiles, in flight
+  const uint32_t rpt_shift = tile_shift - 7u, n_rows = nc << rpt_shift;
+  for (uint32_t r0 = warp * UNROLL; r0 < n_rows; r0 += warps * UNROLL) {
+    int4 v[UNROLL];
+    uint64_t rowi[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        const uint64_t i = base + u * 32u + lane;
-        v[u] = i < n4 ? __ldcv(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
-      }
-      int32_t after = DEAD;  // first symbol after this chunk (needed by lane 31 of the last row)
-      if (lane == 31) { const uint64_t i = base + CHUNK; if (i < n4) after = __ldcv(ids + 4 * i); }
+    for (int u = 0; u < UNROLL; u++) {
+      const uint32_t r = r0 + u;
+      rowi[u] = r < n_rows ? ((static_cast<uint64_t>(cand[r >> rpt_shift]) << rpt_shift) + (r & ((1u << rpt_shift) - 1u))) * 32u : ~0ull;
+      const uint64_t i = rowi[u] + lane;
+      v[u] = (rowi[u] != ~0ull && i < n4) ? __ldcv(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+    }
+    int32_t after[UNROLL];  // first symbol after each row (lane 31's right neighbour)
 #pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
-        const int32_t row_next = (u + 1 < UNROLL) ? __shfl_sync(0xFFFFFFFFu, v[(u + 1 < UNROLL) ? u + 1 : u].x, 0) : after;
-        if (lane == 31) nxt = row_next;
-        uint32_t m = 0;
-        m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
-        m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
-        m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
-        m |= (v[u].w == A && nxt == B) ? 8u : 0u;
-        if (__any_sync(0xFFFFFFFFu, m != 0)) {
-          const uint64_t p0 = (base + u * 32u + lane) * 4u;
-          while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull);
-          }
+    for (int u = 0; u < UNROLL; u++) {
+      after[u] = DEAD;
+      if (lane == 31 && rowi[u] != ~0ull && rowi[u] + 32u < n4) after[u] = __ldcv(ids + 4 * (rowi[u] + 32u));
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
+      if (lane == 31) nxt = after[u];
+      uint32_t m = 0;
+      m |= (v[u].x == A && v[u].y == B) ? 1u : 0u;
+      m |= (v[u].y == A && v[u].z == B) ? 2u : 0u;
+      m |= (v[u].z == A && v[u].w == B) ? 4u : 0u;
+      m |= (v[u].w == A && nxt == B) ? 8u : 0u;
+      if (__any_sync(0xFFFFFFFFu, m != 0)) {
+        const uint64_t p0 = (rowi[u] + lane) * 4u;
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull);
         }
       }
     }
@@ -157,11 +161,11 @@ __global__ void __launch_bounds__(256, 6) k_merge(int4* ids4, uint32_t n4, uint3
       if (cur == A && nxt == B) {
         const int32_t nn = ids[r + 2];
         ids[w] = N;
-        if (planes) plane_set(planes, W, id_cap, N, w);
+        if (planes) plane_set(planes, W, id_cap, tile_shift, N, w);
         ++w; r += 2;
         cur = nn;
       } else {
-        if (w != r) { ids[w] = cur; if (planes) plane_set(planes, W, id_cap, cur, w); }  // a moved symbol may enter another tile
+        if (w != r) { ids[w] = cur; if (planes) plane_set(planes, W, id_cap, tile_shift, cur, w); }  // a moved symbol may enter another tile
         ++w; ++r;
         cur = nxt;
       }
