@@ -90,6 +90,42 @@ __device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, u
   atomicOr(&ctr->err, ERR_DT_FULL);
 }
 
+// The four delta-table updates of one occurrence with their memory round trips overlapped (each update alone is a chain
+// load -> CAS -> list reservation of ~0.5 us links): home-slot loads together, claims together, one list reservation
+// for all newly claimed keys.  A key whose home slot holds another key falls back to the probing dt_add.
+__device__ __forceinline__ void dt_add4(const DeltaTable& dt, DevCounters* ctr, const uint64_t (&key)[4], const int64_t (&delta)[4], const uint64_t (&seq)[4],
+                                        uint32_t valid) {
+  uint64_t slot[4], cur[4], prev[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { slot[j] = mix64(key[j]) & dt.mask; cur[j] = (valid >> j) & 1u ? dt.keys[slot[j]] : 0ull; }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    prev[j] = cur[j];
+    if (((valid >> j) & 1u) && cur[j] == dt.empty)
+      prev[j] = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot[j]]), static_cast<ull>(dt.empty), static_cast<ull>(key[j]));
+  }
+  uint32_t claimed = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] == dt.empty) {
+    if (prev[j] == dt.empty) { claimed |= 1u << j; cur[j] = key[j]; } else cur[j] = prev[j];
+  }
+  if (claimed) {
+    uint32_t idx = atomicAdd(&ctr->dt_n, static_cast<uint32_t>(__popc(claimed)));
+#pragma unroll
+    for (int j = 0; j < 4; j++) if ((claimed >> j) & 1u) {
+      if (idx < dt.cap) { dt.list[idx] = static_cast<uint32_t>(slot[j]); dt.klist[idx] = key[j]; }
+      ++idx;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) if ((valid >> j) & 1u) {
+    if (cur[j] == key[j]) {
+      atomicAdd(&dt.delta[slot[j]], static_cast<ull>(delta[j]));
+      atomicMin(&dt.seq[slot[j]], static_cast<ull>(seq[j]));
+    } else dt_add(dt, ctr, key[j], delta[j], seq[j]);
+  }
+}
+
 __device__ __forceinline__ ull gtime() { ull t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ ulonglong2 ld_ent(const PairEnt* e) { return *reinterpret_cast<const ulonglong2*>(e); }
 

@@ -135,16 +135,12 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, 
   }
   const int64_t c = static_cast<int64_t>(wcnt[wi]);
   const uint64_t seq = seq_base | (p * 4ull);
-  if (l1 >= 0) {
-    const int32_t lid = left_merged ? N : code_to_id(l1, P);
-    dt_add(dt, ctr, fc_key(lid, A), -c, seq + 0);
-    dt_add(dt, ctr, fc_key(lid, N), c, seq + 1);
-  }
-  if (r2 >= 0) {
-    const int32_t rid = code_to_id(r2, P);
-    dt_add(dt, ctr, fc_key(B, rid), -c, seq + 2);
-    dt_add(dt, ctr, fc_key(N, rid), c, seq + 3);
-  }
-  ml[atomicAdd(&ctr->wl_n, 1u)] = static_cast<uint32_t>(p);
+  const int32_t lid = left_merged ? N : code_to_id(l1, P), rid = code_to_id(r2, P);
+  const uint64_t key[4] = {fc_key(lid, A), fc_key(lid, N), fc_key(B, rid), fc_key(N, rid)};
+  const int64_t delta[4] = {-c, c, -c, c};
+  const uint64_t sq[4] = {seq + 0, seq + 1, seq + 2, seq + 3};
+  const uint32_t slot_ml = atomicAdd(&ctr->wl_n, 1u);  // issued before the table updates so its round trip overlaps theirs
+  dt_add4(dt, ctr, key, delta, sq, (l1 >= 0 ? 3u : 0u) | (r2 >= 0 ? 12u : 0u));
+  ml[slot_ml] = static_cast<uint32_t>(p);
   ++my_occ;
 }
