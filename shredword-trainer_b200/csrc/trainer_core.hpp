@@ -43,10 +43,10 @@ class TrainerCore {
   Engine* eng_;
   ExactHeap heap_;
   FlatMap<uint32_t> version_;   // PHANTOM pair key -> current version (absent = 0); phantoms have no device serial
-  std::vector<uint32_t> ver_;   // pair serial -> current version (dense, no hashing on the replay path)
+  HugeArray<uint32_t> ver_;     // pair serial -> current version (dense, no hashing on the replay path)
   uint32_t& ver_of(uint32_t serial, uint64_t key) {
     if (serial == REC_NO_SERIAL) return version_[key];
-    if (serial >= ver_.size()) ver_.resize(std::max<size_t>(serial + 1, ver_.size() * 2 + 1024), 0u);
+    if (serial >= ver_.size()) ver_.ensure(std::max<size_t>(serial + 1, ver_.size() * 2 + 1024));
     return ver_[serial];
   }
   FlatMap<uint64_t> phantom_;   // pair keys containing unk_id -> freq as the reference's table would hold it
