@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(256, 4) k_merge(int4* ids4, uint32_t n4, uint3
   for (uint32_t i = gtid; i < n_keys; i += gthreads) {
     const uint64_t key = dt.klist[i];
     const uint32_t ds = dt.list[i];
-    const ulonglong2 home = ld_ent(&pt.ent[mix64(key) & pt.mask]);
+    const uint64_t home_slot = mix64(key) & pt.mask;
+    const ulonglong2 home = ld_ent(&pt.ent[home_slot]);
+    const uint32_t home_serial = pt.serial[home_slot];  // issued with the entry: a record needs it, and most keys sit in their home slot
     const int64_t d = static_cast<int64_t>(dt.delta[ds]);
     const uint64_t sq = dt.seq[ds];
     dt.keys[ds] = dt.empty; dt.delta[ds] = 0ull; dt.seq[ds] = SEQ_MAX;  // re-arm the scratch slot
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256, 4) k_merge(int4* ids4, uint32_t n4, uint3
       pt.ent[sl].freq = nf;
       if (nf >= P.min_freq) { out.kind = REC_PUSH; out.val = nf; emit = true; }            // bpe.cpp:308-311
       else if (old >= P.min_freq) { out.kind = REC_DEMOTE; out.val = nf; emit = true; }
-      if (emit) out.serial = pt.serial[sl];
+      if (emit) out.serial = (sl == home_slot && home.x == key) ? home_serial : pt.serial[sl];
     }
     if (emit) {
       const uint32_t idx = atomicAdd(&ctr->rec_n, 1u);
