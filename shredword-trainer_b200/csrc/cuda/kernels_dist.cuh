@@ -46,6 +46,14 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
   const uint32_t n_local = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
   if (n_local > INBOX_ENTRIES && gtid == 0) atomicOr(&ctr->err, ERR_INBOX_FULL);
   const uint32_t n_send = n_local < INBOX_ENTRIES ? n_local : static_cast<uint32_t>(INBOX_ENTRIES);
+  bool sent = false;
+  if (gtid == 0) {  // list length and occurrence count travel with the data, under the same fence
+    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
+      InboxHdr* h = reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank));
+      h->n = n_send; h->aux = occ_local;
+    }
+    sent = true;
+  }
   for (uint32_t i = gtid; i < n_send; i += gthreads) {  // P2P stores into every peer's inbox
     const uint32_t ds = dt.list[i];
     const ull k = dt.klist[i], d = dt.delta[ds], sq = dt.seq[ds];
@@ -53,19 +61,15 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
       ull* e = reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR) + 3ull * i;
       e[0] = k; e[1] = d; e[2] = sq;
     }
+    sent = true;
   }
-  __threadfence_system();
+  if (sent) __threadfence_system();  // only threads with stores in flight pay for the system-scope fence
   __syncthreads();
   if (threadIdx.x == 0) last_sender = atomicAdd(&ctr->sent_ctas, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out: announce the list to the peers
+  if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out and fenced: raise the flag at the peers
     __threadfence();
     ctr->sent_ctas = 0;
-    for (int dst = 0; dst < D.world; dst++) if (dst != D.rank) {
-      InboxHdr* h = reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank));
-      h->n = n_send; h->aux = occ_local;
-    }
-    __threadfence_system();
     for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
       *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
   }
