@@ -1,45 +1,48 @@
 // engine_cuda.cu -- the B200 (sm_100a) device engine of the BPE trainer: corpus ingest, pair counting, merge
 // application and pair-table maintenance as hand-written CUDA kernels.  Implements shred::Engine (../engine.hpp).
+// This file holds the host side (buffers, launches, multi-GPU rendezvous); the kernels live in the .cuh fragments
+// included below.
 //
 // Data layout in HBM
 //   ids[]   int32, one flat array holding every unique word back to back in reference word order (A3):
 //             [HDR|wi] s0 s1 ... s(len-1) [DEAD ...]          HDR|wi < -1, symbols >= 0, DEAD == -1
-//           A word keeps its slot between compactions; merges left-pack its live symbols and fill the tail with DEAD.
-//           Because words are stored in reference scan order, "flat position" is monotone in the reference's
+//           A word keeps its slot range between compactions; merges left-pack its live symbols and fill the tail with
+//           DEAD.  Because words are stored in reference scan order, "flat position" is monotone in the reference's
 //           (word index, position) order and serves as the sequence number the host needs (Appendix A14).
-//   wcnt[]  uint64 word counts, woff[] uint64 slot offsets (N+1), wlen[] uint32 live lengths.
-//   pair table   open addressing, uint64 key (first<<32|second) -> uint64 freq        (reference BIMap, hash.cpp:104-130)
-//   delta table  open addressing scratch, key -> (sum of +/-count, min sequence)      (reference FreqChangeMap, bpe.cpp:9-38)
+//   wid[]   uint32 word index per slot; wcnt[] uint64 word counts, woff[] uint64 slot offsets (N+1), wlen[] uint32 lengths
+//   planes  tile occurrence index (one bit plane per token id; a merge scans only tiles holding both tokens)
+//   pair table   open addressing, uint64 key (first<<32|second) -> uint64 freq + serial  (reference BIMap, hash.cpp:104-130)
+//   delta table  open addressing scratch, key -> (sum of +/-count, min sequence)         (reference FreqChangeMap, bpe.cpp:9-38)
 //
-// Kernels (reference loop each one replaces)
-//   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise on \t\r\n space, unique-word table insert
-//   k_hist ............ histogram.cpp:30-36                unweighted byte histogram over unique words
-//   k_scatter/k_sort_buckets  hash.cpp:61-72               word order = (djb2 & 4095, first occurrence)
-//   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids with unk substitution
-//   k_count ........... bpe.cpp:187-218                    adjacent pair counts
-//   k_merge ........... bpe.cpp:265-318                    one cooperative launch per merge: HBM-bound scan of the candidate tiles
-//                                                          with per-occurrence count deltas | grid barrier | deltas folded into the
-//                                                          pair table + records published | in-place rewrite of the touched words
-//   k_token_freq ...... bpe.cpp:409-415                    final token frequencies
+// Kernels (reference loop each one replaces)                                               file
+//   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise, unique-word table     kernels_ingest.cuh
+//   k_hist_words ...... histogram.cpp:30-36                unweighted byte histogram        kernels_ingest.cuh
+//   k_scatter/k_sort_buckets  hash.cpp:61-72               word order (djb2 & 4095, first)  kernels_ingest.cuh
+//   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids, unk substitution   kernels_ingest.cuh
+//   k_count ........... bpe.cpp:187-218                    adjacent pair counts             kernels_count.cuh
+//   k_finalize_count .. bpe.cpp:219-227                    fold counts, seed records        kernels_fold.cuh
+//   k_merge ........... bpe.cpp:265-318                    one cooperative launch per merge kernels_merge.cuh
+//                       scan of the candidate tiles with per-occurrence count deltas | grid barrier | deltas folded
+//                       into the pair table + records published | in-place rewrite of the touched words
+//   exchange_deltas ... (multi-GPU) per-merge delta exchange over NVLink peer memory        kernels_dist.cuh
+//   k_token_freq ...... bpe.cpp:409-415                    final token frequencies          kernels_merge.cuh
 #include <cuda_runtime.h>
-
-#include <chrono>
-#include <cstdint>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <vector>
-
-#include "../../../include/shred_abi.h"
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
+#include "../../../include/shred_abi.h"
 #include "../charset.hpp"
 #include "../engine.hpp"
 #include "../shard.hpp"
