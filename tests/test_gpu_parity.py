@@ -289,3 +289,27 @@ def test_midsize_configs_match_oracle(name, gen, cfg, T, tmp_path):
     if cfg[1] < 0 or cfg[1] < 256 + n:
         assert open(vo, "rb").read() == open(vg, "rb").read()
     t.destroy(); o.destroy()
+
+
+def test_api_corner_cases(T, tmp_path):
+    data = open(os.path.join(os.path.dirname(__file__), "golden", "kat_py.txt"), "rb").read()
+    # save right after load (no training): 256 byte tokens with their corpus frequencies, empty model
+    o = Oracle(300, 0, 0.995, 2); o.load_bytes(data)
+    t = T(300, 0, 0.995, 2); t.load_bytes(data)
+    mo, vo, mg, vg = (str(tmp_path / x) for x in ("mo", "vo", "mg", "vg"))
+    o.save(mo, vo); t.save(mg, vg)
+    assert open(mg, "rb").read() == b"" and open(vo, "rb").read() == open(vg, "rb").read()
+    # merge_batch before bpe_init: the heap is empty, nothing happens (reference bpe.cpp:237-240)
+    assert t.merge_batch(5) == 0 and t.num_merges == 0
+    # vocab_size 256 and 257: zero and exactly one merge
+    for vs in (256, 257):
+        a, b = T(vs, 0, 0.995, 2), Oracle(vs, 0, 0.995, 2)
+        a.load_bytes(data); b.load_bytes(data)
+        assert a.train() == b.train() == vs - 256 and a.merges() == b.merges()
+        a.destroy(); b.destroy()
+    # a trainer that never loads anything can train, save and be destroyed
+    e = T(300)
+    assert e.train() == 0
+    e.save(str(tmp_path / "em"), str(tmp_path / "ev"))
+    assert (tmp_path / "ev").read_bytes().count(b"\n") == 257 and (tmp_path / "em").read_bytes() == b""
+    e.destroy(); t.destroy(); o.destroy()
