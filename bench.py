@@ -335,6 +335,12 @@ def main():
                 line["cpu_baseline"] = reference_sample(corpus, (vocab, unk, cov, mf))
             except Exception as e:  # the checker must never take the measurement down
                 line["cpu_baseline"] = {"value": None, "unit": "merges/s", "cores": 1, "kind": "unavailable", "sample": str(e)}
+            try:  # the one full-size run of the unmodified reference on this workload, recorded beside its golden vector
+                full = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"][args.workload].get("reference_full_run")
+                if full:
+                    line["cpu_baseline"]["full_workload_recorded"] = dict(full, merges_per_s=full["merges"] / full["train_s"], note="not timed in this run")
+            except Exception:
+                pass
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
