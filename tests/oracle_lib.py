@@ -28,7 +28,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "bpe_oracle.c")):
+    if not os.path.exists(ORACLE_SO) or any(os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("bpe_oracle.c", "bpe_encode_oracle.c")):
         build_oracle()
     L = ctypes.CDLL(ORACLE_SO)
     vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32
@@ -53,6 +53,17 @@ def lib():
     L.oracle_get_pairs.argtypes, L.oracle_get_pairs.restype = [vp, ctypes.POINTER(i32), ctypes.POINTER(u64), u64], u64
     L.oracle_get_heap.argtypes, L.oracle_get_heap.restype = [vp, ctypes.POINTER(i32), ctypes.POINTER(u64), u64], u64
     L.oracle_stats.argtypes, L.oracle_stats.restype = [vp, ctypes.POINTER(u64)], None
+    # encoder oracle (oracle/bpe_encode_oracle.c)
+    L.enc_oracle_create.argtypes, L.enc_oracle_create.restype = [ctypes.POINTER(i32), ctypes.c_size_t], vp
+    L.enc_oracle_load.argtypes, L.enc_oracle_load.restype = [ctypes.c_char_p], vp
+    L.enc_oracle_destroy.argtypes, L.enc_oracle_destroy.restype = [vp], None
+    L.enc_oracle_encode.argtypes, L.enc_oracle_encode.restype = [vp, ctypes.c_char_p, u64], ctypes.c_int
+    L.enc_oracle_encode_word.argtypes, L.enc_oracle_encode_word.restype = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(i32)], ctypes.c_size_t
+    for name in ("enc_oracle_n_tokens", "enc_oracle_n_ids", "enc_oracle_vocab_size"):
+        getattr(L, name).argtypes, getattr(L, name).restype = [vp], u64
+    L.enc_oracle_ids.argtypes, L.enc_oracle_ids.restype = [vp], ctypes.POINTER(i32)
+    L.enc_oracle_offsets.argtypes, L.enc_oracle_offsets.restype = [vp], ctypes.POINTER(u64)
+    L.enc_oracle_decode.argtypes, L.enc_oracle_decode.restype = [vp, ctypes.POINTER(i32), u64, ctypes.c_char_p, u64], ctypes.c_int64
     _lib = L
     return L
 
@@ -198,3 +209,53 @@ def run_reference(corpus_path, vocab_size, unk_id, coverage, min_pair_freq, outd
     merges = open(mp, "rb").read()
     vocab = open(vp, "rb").read() if os.path.exists(vp) else b""
     return merges, vocab, info
+
+
+class EncodeOracle:
+    """The reference's Python encoder (shredword/utils/bpe.py:191-225) restated in C for the trainer's model file."""
+
+    def __init__(self, merges=None, model_path=None):
+        self.L = lib()
+        if model_path is not None:
+            self.h = self.L.enc_oracle_load(os.fsencode(model_path))
+        else:
+            flat = [x for m in merges for x in m]
+            arr = (ctypes.c_int32 * max(len(flat), 1))(*flat)
+            self.h = self.L.enc_oracle_create(arr, len(merges))
+        if not self.h:
+            raise ValueError("invalid BPE model")
+
+    def encode(self, data: bytes):
+        """-> (ids, offsets): ids of all words back to back, offsets[i] = index of word i's first id (len = words + 1)"""
+        self.L.enc_oracle_encode(self.h, data, len(data))
+        n, t = self.L.enc_oracle_n_ids(self.h), self.L.enc_oracle_n_tokens(self.h)
+        return list(self.L.enc_oracle_ids(self.h)[:n]), list(self.L.enc_oracle_offsets(self.h)[:t + 1])
+
+    def encode_bytes(self, data: bytes):
+        """ids and offsets as little-endian byte strings (for hashing large results)"""
+        self.L.enc_oracle_encode(self.h, data, len(data))
+        n, t = self.L.enc_oracle_n_ids(self.h), self.L.enc_oracle_n_tokens(self.h)
+        return ctypes.string_at(self.L.enc_oracle_ids(self.h), 4 * n), ctypes.string_at(self.L.enc_oracle_offsets(self.h), 8 * (t + 1))
+
+    def encode_word(self, word: bytes):
+        out = (ctypes.c_int32 * max(len(word), 1))()
+        n = self.L.enc_oracle_encode_word(self.h, word, len(word), out)
+        return list(out[:n])
+
+    def decode(self, ids):
+        arr = (ctypes.c_int32 * max(len(ids), 1))(*ids)
+        n = self.L.enc_oracle_decode(self.h, arr, len(ids), None, 0)
+        if n < 0:
+            raise ValueError("invalid token id")
+        buf = ctypes.create_string_buffer(max(n, 1))
+        self.L.enc_oracle_decode(self.h, arr, len(ids), buf, n)
+        return buf.raw[:n]
+
+    @property
+    def vocab_size(self):
+        return self.L.enc_oracle_vocab_size(self.h)
+
+    def destroy(self):
+        if self.h:
+            self.L.enc_oracle_destroy(self.h)
+            self.h = None
