@@ -128,6 +128,38 @@ SHRED_API uint64_t bpe_b200_get_pairs(const Trainer* trainer, int32_t* ab_out, u
 /* Human-readable description of the device the trainer runs on ("NVIDIA B200 sm_100 148 SMs"). */
 SHRED_API const char* bpe_b200_device_name(void);
 
+/* ---- encoder: the caller-side step after bpe_save ---------------------------------
+ * The reference has no FFI for this: its encoder is the pure-Python BPETokenizer (shredword/utils/bpe.py).  These entry
+ * points replace, for the model file bpe_save writes (bpe.cpp:419-427):
+ *   bpe_b200_encoder_load / _create   BaseTokenizer.load            utils/bpe.py:140-155  (merges[(a, b)] = id in file order)
+ *   bpe_b200_encode (+ _fetch)        BPETokenizer.encode           utils/bpe.py:205-212  with _encode_chunk :191-203 per word
+ *   bpe_b200_decode                   BPETokenizer.decode           utils/bpe.py:214-225  (bytes; an unknown id is an error)
+ * Words are the trainer's: maximal runs of bytes outside {9, 10, 13, 32} (bpe.cpp:131-152); delimiters produce no ids.
+ * A model is accepted iff row m is {a, b, 256 + m} with 0 <= a, b < 256 + m; otherwise create/load return NULL. */
+typedef struct shred_encoder shred_encoder_t;
+typedef struct shred_encode_stats {
+  uint64_t text_bytes, n_words, n_unique_words, n_ids;
+  uint64_t pool_ids;          /* symbols of the distinct words before merging */
+  uint64_t kernel_launches, h2d_bytes, d2h_bytes;
+  double h2d_ms;              /* text -> HBM */
+  double tokenize_ms, words_ms, expand_ms; /* CUDA events: distinct words | merge loop per distinct word | occurrences -> ids */
+  double device_ms;           /* CUDA events around the three phases */
+  double encode_wall_ms;      /* host clock around bpe_b200_encode */
+  double d2h_ms;              /* bpe_b200_encode_fetch */
+} shred_encode_stats_t;
+SHRED_API shred_encoder_t* bpe_b200_encoder_create(const int32_t* triples, size_t n_merges);
+SHRED_API shred_encoder_t* bpe_b200_encoder_load(const char* model_path);
+SHRED_API void bpe_b200_encoder_destroy(shred_encoder_t* enc);
+SHRED_API size_t bpe_b200_encoder_vocab_size(const shred_encoder_t* enc);
+/* Encodes a host buffer; the ids of all words back to back and their CSR offsets (n_words + 1) stay in HBM.  0 / -1. */
+SHRED_API int bpe_b200_encode(shred_encoder_t* enc, const uint8_t* text, uint64_t n_bytes, uint64_t* n_words, uint64_t* n_ids);
+/* Copies the last result out: ids_out[n_ids], offsets_out[n_words + 1] (either may be NULL).  0 / -1. */
+SHRED_API int bpe_b200_encode_fetch(shred_encoder_t* enc, int32_t* ids_out, uint64_t* offsets_out);
+/* Bytes of the ids back to back into out[cap].  Returns the byte count (nothing written if > cap), -2 for an id outside
+ * [0, vocab_size), -1 on a device error. */
+SHRED_API int64_t bpe_b200_decode(shred_encoder_t* enc, const int32_t* ids, uint64_t n_ids, uint8_t* out, uint64_t cap);
+SHRED_API int bpe_b200_encoder_get_stats(const shred_encoder_t* enc, shred_encode_stats_t* out);
+
 /* ---- Unigram symbols: reference unigram.h:50-68.  Stubs; every call reports failure. -------------------------- */
 typedef struct UnigramTrainer UnigramTrainer;
 SHRED_API UnigramTrainer* trainerCreate(int vocab_size, float character_coverage, int max_len, int seed_size); /* returns NULL */

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Build every native artefact of the B200 BPE trainer IN-TREE (they travel to the GPU box with the snapshot).
 
-  shredword/lib/libtrainer.so   CUDA (sm_100a) + host control + C ABI   -- what shredword/cbase.py loads
+  shredword/lib/libtrainer.so   CUDA (sm_100a) trainer + encoder, host control, C ABI   -- what shredword/cbase.py loads
   build/trainer.exe             CLI drop-in (csrc/cli_main.cpp), linked against libtrainer.so
   build/gen_corpus              synthetic corpus generator (tools/gen_corpus.c)
 
@@ -37,9 +37,9 @@ def _run(cmd):
 def build(force=False, verbose_ptxas=False):
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    srcs = [os.path.join(CSRC, "abi.cpp"), os.path.join(CSRC, "trainer_core.cpp"), os.path.join(CSRC, "cuda", "engine_cuda.cu")]
+    srcs = [os.path.join(CSRC, "abi.cpp"), os.path.join(CSRC, "trainer_core.cpp"), os.path.join(CSRC, "cuda", "engine_cuda.cu"), os.path.join(CSRC, "cuda", "encoder_cuda.cu")]
     deps = srcs + [os.path.join(CSRC, h) for h in ("engine.hpp", "trainer_core.hpp", "exact_heap.hpp", "flat_map.hpp", "charset.hpp", "shard.hpp")] + \
-        [os.path.join(CSRC, "cuda", h) for h in ("common.cuh", "kernels_ingest.cuh", "kernels_count.cuh", "kernels_fold.cuh", "kernels_dist.cuh", "kernels_merge.cuh")] + \
+        [os.path.join(CSRC, "cuda", h) for h in ("common.cuh", "kernels_tokenize.cuh", "kernels_scan.cuh", "kernels_ingest.cuh", "kernels_count.cuh", "kernels_fold.cuh", "kernels_dist.cuh", "kernels_merge.cuh", "kernels_encode.cuh")] + \
         [os.path.join(ROOT, "include", "shred_abi.h")]
     if force or _stale(LIB, deps):
         _run(["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-shared", "-o", LIB] + srcs)

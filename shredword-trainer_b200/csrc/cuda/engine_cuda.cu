@@ -15,7 +15,7 @@
 //   delta table  open addressing scratch, key -> (sum of +/-count, min sequence)         (reference FreqChangeMap, bpe.cpp:9-38)
 //
 // Kernels (reference loop each one replaces)                                               file
-//   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise, unique-word table     kernels_ingest.cuh
+//   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise, unique-word table     kernels_tokenize.cuh
 //   k_hist_words ...... histogram.cpp:30-36                unweighted byte histogram        kernels_ingest.cuh
 //   k_scatter/k_sort_buckets  hash.cpp:61-72               word order (djb2 & 4095, first)  kernels_ingest.cuh
 //   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids, unk substitution   kernels_ingest.cuh
@@ -51,6 +51,8 @@ namespace shred {
 namespace {
 
 #include "common.cuh"
+#include "kernels_tokenize.cuh"
+#include "kernels_scan.cuh"
 #include "kernels_ingest.cuh"
 #include "kernels_count.cuh"
 #include "kernels_fold.cuh"

@@ -1,92 +1,8 @@
-// kernels_ingest.cuh -- corpus ingest: tokenise + unique-word table, reference word order, histogram, symbolise; fills; device-wide scan.
+// kernels_ingest.cuh -- corpus ingest after tokenisation (kernels_tokenize.cuh): reference word order, histogram, symbolise; fills.
 // Fragment of engine_cuda.cu: included inside `namespace shred { namespace {`, in the order listed there.
 #pragma once
 
 // ------------------------------------------------------------------------------------------------------------ ingest
-
-struct WordTable {
-  ull* tag;       // 0 = empty
-  ull* first;     // smallest byte offset of an occurrence
-  ull* count;
-  uint32_t* len;
-  uint32_t* bucket;  // djb2 & 4095
-  uint64_t mask, cap;
-};
-
-// Each thread owns 16 consecutive corpus bytes (one uint4 load) and inserts every token that STARTS inside them.
-// text is padded with >= 32 spaces, so token walks terminate.
-__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
-  const uint64_t n16 = (n + 15) >> 4;
-  uint32_t my_tokens = 0;
-  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n16; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t base = t << 4;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t prev = base ? text[base - 1] : 32u;
-    // a NUL byte hides the rest of its line in the reference (fgets + strlen, bpe.cpp:131-147): report it, the host
-    // blanks the hidden spans and loads again
-    if (((v.x - 0x01010101u) & ~v.x & 0x80808080u) | ((v.y - 0x01010101u) & ~v.y & 0x80808080u) | ((v.z - 0x01010101u) & ~v.z & 0x80808080u) |
-        ((v.w - 0x01010101u) & ~v.w & 0x80808080u))
-      atomicOr(&ctr->err, ERR_HAS_NUL);
-    // delimiter mask of my 16 bytes
-    uint32_t dm = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) { uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 255u; dm |= (is_delim(c) ? 1u : 0u) << i; }
-    uint32_t starts = ~dm & ((dm << 1) | (is_delim(prev) ? 1u : 0u)) & 0xFFFFu;
-    while (starts) {
-      const int i = __ffs(starts) - 1;
-      starts &= starts - 1;
-      const uint64_t off = base + i;
-      if (off >= n) break;
-      // walk the token: two 32-bit multiplicative hashes (placement tag) + djb2 (reference bucket, hash.cpp:35-39)
-      uint32_t h1 = 2166136261u ^ seed, h2 = 0x9E3779B9u + seed, dj = 5381u, len = 0;
-      for (;;) {
-        const uint32_t c = text[off + len];
-        if (is_delim(c)) break;
-        h1 = (h1 ^ c) * 16777619u;
-        h2 = (h2 + c) * 0x85EBCA6Bu; h2 ^= h2 >> 15;
-        dj = dj * 33u + c;
-        ++len;
-      }
-      ++my_tokens;
-      const uint64_t tag = mix64((static_cast<uint64_t>(h1) << 32) | h2 | 0) | 1ull;
-      uint64_t slot = tag & wt.mask;
-      bool done = false;
-      for (uint32_t probe = 0; probe < 8192u && !done; ++probe) {
-        ull cur = wt.tag[slot];
-        if (cur == 0ull) {
-          ull prevt = atomicCAS(&wt.tag[slot], 0ull, static_cast<ull>(tag));
-          if (prevt == 0ull) {  // claimed: publish the immutable facts
-            wt.len[slot] = len;
-            wt.bucket[slot] = dj & 4095u;
-            atomicAdd(&ctr->n_unique, 1u);
-            cur = tag;
-          } else cur = prevt;
-        }
-        if (cur == tag) {
-          // first occurrence: most tokens come after the word's first sighting, so look before paying for an atomic
-          ull old = *reinterpret_cast<volatile ull*>(&wt.first[slot]);
-          if (off < old) old = atomicMin(&wt.first[slot], static_cast<ull>(off));
-          {  // count: lanes of this warp that hit the same slot right now add once (hot words are most of a Zipf corpus)
-            const unsigned am = __activemask();
-            const unsigned grp = __match_any_sync(am, slot);
-            if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(grp) - 1)) atomicAdd(&wt.count[slot], static_cast<ull>(__popc(grp)));
-          }
-          if (old != SEQ_MAX && old != off) {  // same tag: must be the same bytes, else retry ingest with a new seed
-            bool same = is_delim(text[old + len]);
-            for (uint32_t j = 0; j < len && same; j++) same = text[old + j] == text[off + j];
-            if (!same) atomicOr(&ctr->err, ERR_WT_COLLISION);
-          }
-          done = true;
-        } else slot = (slot + 1) & wt.mask;
-      }
-      if (!done) atomicOr(&ctr->err, ERR_WT_FULL);
-    }
-  }
-  // token count: warp reduce, one atomic per warp
-  for (int o = 16; o; o >>= 1) my_tokens += __shfl_down_sync(0xFFFFFFFFu, my_tokens, o);
-  if ((threadIdx.x & 31) == 0 && my_tokens) atomicAdd(&ctr->n_tokens, static_cast<ull>(my_tokens));
-}
 
 // unique slots -> dense list + per-bucket population
 __global__ void k_collect(WordTable wt, uint32_t* u_slot, uint32_t* u_n, uint32_t* bucket_cnt) {
@@ -204,53 +120,4 @@ __global__ void k_fill_i32(int32_t* p, uint64_t from, uint64_t to, int32_t v) {
 }
 __global__ void k_fill_u64(ull* p, uint64_t n, ull v) {
   for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) p[i] = v;
-}
-
-// ---- device-wide exclusive scan of uint64 (three passes; 2048 items per block) used at load and at compaction
-constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
-
-__device__ __forceinline__ ull block_excl_scan(ull v, ull* total) {  // 256 threads
-  __shared__ ull wsum[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  ull x = v;
-  for (int o = 1; o < 32; o <<= 1) { ull y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
-  if (lane == 31) wsum[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    ull s = lane < 8 ? wsum[lane] : 0;
-    for (int o = 1; o < 8; o <<= 1) { ull y = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += y; }
-    if (lane < 8) wsum[lane] = s;
-  }
-  __syncthreads();
-  const ull before = warp ? wsum[warp - 1] : 0;
-  *total = wsum[7];
-  __syncthreads();
-  return before + x - v;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const ull* in, uint64_t n, ull* sums) {
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
-  ull s = 0;
-  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += in[base + i];
-  ull total;
-  block_excl_scan(s, &total);
-  if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(ull* sums, uint32_t nb, ull* grand_total) {  // one block
-  ull carry = 0;
-  for (uint32_t base = 0; base < nb; base += SCAN_THREADS) {
-    const uint32_t i = base + threadIdx.x;
-    ull v = i < nb ? sums[i] : 0, total;
-    ull ex = block_excl_scan(v, &total);
-    if (i < nb) sums[i] = carry + ex;
-    carry += total;
-  }
-  if (threadIdx.x == 0) *grand_total = carry;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const ull* in, uint64_t n, const ull* sums, ull* out) {
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_ITEMS;
-  ull v[SCAN_ITEMS], s = 0;
-  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
-  ull total;
-  ull run = sums[blockIdx.x] + block_excl_scan(s, &total);
-  for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = run; run += v[i]; }
 }

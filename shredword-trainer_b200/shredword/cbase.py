@@ -8,7 +8,7 @@ There is deliberately no fallback: if the CUDA library is missing, importing thi
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 
@@ -91,3 +91,22 @@ lib.bpe_b200_get_words.argtypes, lib.bpe_b200_get_words.restype = [POINTER(Train
 lib.bpe_b200_get_charset.argtypes, lib.bpe_b200_get_charset.restype = [POINTER(Trainer), POINTER(c_uint8), POINTER(c_uint64)], c_int
 lib.bpe_b200_get_pairs.argtypes, lib.bpe_b200_get_pairs.restype = [POINTER(Trainer), POINTER(c_int32), POINTER(c_uint64), c_uint64], c_uint64
 lib.bpe_b200_device_name.argtypes, lib.bpe_b200_device_name.restype = [], c_char_p
+
+
+class EncodeStats(Structure):  # include/shred_abi.h shred_encode_stats_t
+    _fields_ = [(n, c_uint64) for n in ("text_bytes", "n_words", "n_unique_words", "n_ids", "pool_ids", "kernel_launches", "h2d_bytes", "d2h_bytes")] + \
+               [(n, c_double) for n in ("h2d_ms", "tokenize_ms", "words_ms", "expand_ms", "device_ms", "encode_wall_ms", "d2h_ms")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# encoder (include/shred_abi.h; replaces the reference's pure-Python BPETokenizer, shredword/utils/bpe.py:157-225)
+lib.bpe_b200_encoder_create.argtypes, lib.bpe_b200_encoder_create.restype = [POINTER(c_int32), c_size_t], c_void_p
+lib.bpe_b200_encoder_load.argtypes, lib.bpe_b200_encoder_load.restype = [c_char_p], c_void_p
+lib.bpe_b200_encoder_destroy.argtypes, lib.bpe_b200_encoder_destroy.restype = [c_void_p], None
+lib.bpe_b200_encoder_vocab_size.argtypes, lib.bpe_b200_encoder_vocab_size.restype = [c_void_p], c_size_t
+lib.bpe_b200_encode.argtypes, lib.bpe_b200_encode.restype = [c_void_p, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)], c_int
+lib.bpe_b200_encode_fetch.argtypes, lib.bpe_b200_encode_fetch.restype = [c_void_p, c_void_p, c_void_p], c_int
+lib.bpe_b200_decode.argtypes, lib.bpe_b200_decode.restype = [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64], c_int64
+lib.bpe_b200_encoder_get_stats.argtypes, lib.bpe_b200_encoder_get_stats.restype = [c_void_p, POINTER(EncodeStats)], c_int
