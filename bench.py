@@ -135,6 +135,60 @@ def reference_sample(corpus_path, cfg, steps=1, warmup=0):
             "load_s": load_s, "train_s": train_s, "merges": merges, "sample_bytes": nbytes}
 
 
+def encoder_leg(host, size, merges, peak_hint=None, with_cpu=True, reps=3):
+    """SURVEY 8f rank 2, informational: encode the bench corpus with the model just trained (bpe_b200_encode through the C
+    ABI, pinned host text in, pinned host ids + offsets out), and the CPU oracle on a bounded sample beside it."""
+    import torch
+    from shredword import BPEEncoder
+    enc = BPEEncoder(merges=merges)
+    n_words, n_ids = enc.encode_raw(host.data_ptr(), size)   # warm-up 1; sizes of the result
+    ids = torch.empty(max(n_ids, 1), dtype=torch.int32, pin_memory=True)
+    off = torch.empty(n_words + 1, dtype=torch.int64, pin_memory=True)
+    enc.fetch_raw(ids.data_ptr(), off.data_ptr())
+    for _ in range(2):                                         # warm-ups 2, 3
+        enc.encode_raw(host.data_ptr(), size)
+        enc.fetch_raw(ids.data_ptr(), off.data_ptr())
+    walls, sts = [], []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enc.encode_raw(host.data_ptr(), size)
+        enc.fetch_raw(ids.data_ptr(), off.data_ptr())
+        walls.append(time.perf_counter() - t0)
+        sts.append(enc.stats())
+    wall = sum(walls) / reps
+    st = {k: sum(x[k] for x in sts) / reps for k in sts[0]}
+    # occurrence phase (count starts + lookup + scans + expand): text read, ids and offsets written
+    expand_bytes = size + 4.0 * n_ids + 8.0 * (n_words + 1)
+    out = {"what": "bpe_b200_encode + bpe_b200_encode_fetch on the whole bench corpus with the merges of the last timed step; 3 warm-ups, mean of %d runs" % reps,
+           "text_bytes": size, "n_words": n_words, "n_unique_words": int(st["n_unique_words"]), "n_ids": n_ids, "ids_per_word": n_ids / max(n_words, 1),
+           "e2e_words_per_s": n_words / wall, "e2e_text_gbs": size / wall / 1e9, "e2e_s": wall,
+           "h2d_bytes": size, "d2h_bytes": 4 * n_ids + 8 * (n_words + 1),
+           "device_words_per_s": n_words / (st["device_ms"] * 1e-3), "device_text_gbs": size / (st["device_ms"] * 1e-3) / 1e9,
+           "device_ms": st["device_ms"], "device_ms_runs": [round(x["device_ms"], 3) for x in sts], "e2e_s_runs": [round(x, 5) for x in walls], "tokenize_ms": st["tokenize_ms"], "words_ms": st["words_ms"], "expand_ms": st["expand_ms"],
+           "h2d_ms": st["h2d_ms"], "d2h_ms": st["d2h_ms"], "kernel_launches": int(st["kernel_launches"]),
+           "expand_algorithmic_bytes": expand_bytes, "expand_algorithmic_gbs": expand_bytes / (st["expand_ms"] * 1e-3) / 1e9 if st["expand_ms"] else None}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import EncodeOracle
+        sample = bytes(host[:min(size, REF_SAMPLE_BYTES)].numpy())
+        o = EncodeOracle(merges)
+        t0 = time.perf_counter()
+        oi, oo = o.encode_bytes(sample)
+        cpu_s = time.perf_counter() - t0
+        o.destroy()
+        import hashlib
+        sw, si = enc.encode_raw(host.data_ptr(), len(sample))
+        enc.fetch_raw(ids.data_ptr(), off.data_ptr())
+        same = hashlib.md5(oi).digest() == hashlib.md5(ids[:si].numpy().tobytes()).digest() and hashlib.md5(oo).digest() == hashlib.md5(off[:sw + 1].numpy().tobytes()).digest()
+        out["cpu_baseline"] = {"value": sw / cpu_s, "unit": "words/s", "cores": 1, "kind": "port",
+                               "sample": "first %d bytes of the corpus through oracle/bpe_encode_oracle.c (C restatement of the reference's Python _encode_chunk, "
+                                         "with a distinct-word cache the Python reference does not have)" % len(sample),
+                               "bit_exact_vs_oracle_on_sample": bool(same)}
+    enc.destroy()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -258,6 +312,12 @@ def main():
         dist.all_reduce(rt, op=dist.ReduceOp.MAX)
         replicas = {"what": f"{world} independent trainers (one per GPU) on the same workload, 1 step, max over ranks",
                     "value": world * rstep[0] / (rt[0].item() * 1e-3), "e2e": world * rstep[0] / rt[1].item(), "unit": "merges/s", "scaling": "weak"}
+    encoder = None
+    if world == 1:
+        try:
+            encoder = encoder_leg(host, size, steps[-1][4], peak_hint=None, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:  # informational leg: never takes the headline measurement down
+            encoder = {"error": str(e)}
     merges = steps[0][0]
     train_dev_ms = sum(s[3]["train_device_ms"] for s in steps)
     e2e_s = sum(s[1] + s[2] for s in steps)
@@ -319,6 +379,10 @@ def main():
     }
     if replicas:
         line["detail"]["replicas"] = replicas
+    if encoder:
+        if "expand_algorithmic_gbs" in encoder and peak:
+            encoder["expand_frac_of_hbm_peak"] = encoder["expand_algorithmic_gbs"] / peak
+        line["detail"]["encoder"] = encoder
     try:
         big = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"].get(args.workload)
         if big:

@@ -4,12 +4,11 @@
 //
 // Pipeline of one bpe_b200_encode call (all on the encoder's stream):
 //   text -> HBM (padded with spaces)
-//   k_tokenize            distinct words of the text (the trainer's own tokeniser + word table)      kernels_tokenize.cuh
+//   k_enc_count_starts + scan   occurrences per 4 KB unit -> index of every occurrence in text order
+//   k_enc_tokenize        distinct words of the text (the trainer's tokeniser + word table); every occurrence notes its word
 //   k_enc_collect + scan  dense list of distinct words, pool offsets
 //   k_enc_words           one warp per distinct word: the reference's merge loop, in place            kernels_encode.cuh
-//   k_enc_count_starts + scan   occurrences per 4 KB unit -> index of every occurrence in text order
-//   k_enc_lookup          occurrence -> (encoded length, pool position) of its word
-//   scan                  encoded lengths -> CSR offsets of the output
+//   k_enc_toklen + scan   encoded lengths -> CSR offsets of the output
 //   k_expand<int32>       occurrences copy their word's ids; stores coalesced over the output
 // Results stay in HBM until bpe_b200_encode_fetch copies them out.  There is no CPU path: without a usable sm_100 device
 // bpe_b200_encoder_create fails.
@@ -115,21 +114,20 @@ class CudaEncoder {
 
   int encode(const uint8_t* text, uint64_t n, uint64_t* n_words_out, uint64_t* n_ids_out) {
     CK(cudaSetDevice(dev_));
-    drop_result();
+    have_result_ = false; n_ids_ = 0; n_tok_ = 0;
     std::memset(&stats_, 0, sizeof stats_);
     launches_ = 0;
     const double t_begin = now_ms();
     const uint64_t padded = ((n + 15) & ~15ull) + 64;
     uint8_t* d_text = nullptr;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_text), padded, st_));
+    RC(need(b_text_, padded, &d_text));
     if (n) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
     CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
     CK(cudaStreamSynchronize(st_));
     stats_.h2d_ms = now_ms() - t_begin;
     stats_.h2d_bytes = n;
-    int rc = encode_device(d_text, n);
-    afree(d_text);
-    if (rc != 0) { drop_result(); return rc; }
+    RC(encode_device(d_text, n));
+    have_result_ = true;
     stats_.encode_wall_ms = now_ms() - t_begin;
     stats_.text_bytes = n; stats_.n_words = n_tok_; stats_.n_ids = n_ids_; stats_.kernel_launches = launches_;
     if (n_words_out) *n_words_out = n_tok_;
@@ -154,9 +152,9 @@ class CudaEncoder {
   int64_t decode(const int32_t* ids, uint64_t n, uint8_t* out, uint64_t cap) {
     if (cudaSetDevice(dev_) != cudaSuccess) return -1;
     if (n == 0) return 0;
-    int32_t* d_in = nullptr; ull *d_len = nullptr, *d_src = nullptr, *d_sums = nullptr; uint8_t* d_out = nullptr;
+    int32_t* d_in = nullptr; ull *d_len = nullptr, *d_src = nullptr; uint8_t* d_out = nullptr;
     uint32_t* bad = reinterpret_cast<uint32_t*>(scal_ + 2);
-    auto cleanup = [&]() { afree(d_in); afree(d_len); afree(d_src); afree(d_sums); afree(d_out); cudaStreamSynchronize(st_); };
+    auto cleanup = [&]() { afree(d_in); afree(d_len); afree(d_src); afree(d_out); cudaStreamSynchronize(st_); };
     auto body = [&]() -> int64_t {
       CK(cudaMallocAsync(reinterpret_cast<void**>(&d_in), n * 4, st_));
       CK(cudaMallocAsync(reinterpret_cast<void**>(&d_len), (n + 1) * 8, st_));
@@ -164,7 +162,7 @@ class CudaEncoder {
       CK(cudaMemcpyAsync(d_in, ids, n * 4, cudaMemcpyHostToDevice, st_));
       CK(cudaMemsetAsync(bad, 0, 4, st_));
       k_dec_lens<<<grid_for(n, 256), 256, 0, st_>>>(d_in, n, d_toff_, static_cast<uint32_t>(vocab_size()), d_len, d_src, bad);
-      RC(scan_in_place(d_len, n, &d_sums));
+      RC(scan_in_place(d_len, n));
       ull total = 0; uint32_t is_bad = 0;
       CK(cudaMemcpyAsync(&total, d_len + n, 8, cudaMemcpyDeviceToHost, st_));
       CK(cudaMemcpyAsync(&is_bad, bad, 4, cudaMemcpyDeviceToHost, st_));
@@ -172,7 +170,7 @@ class CudaEncoder {
       if (is_bad) return -2;
       if (total > cap || total == 0) return static_cast<int64_t>(total);
       CK(cudaMallocAsync(reinterpret_cast<void**>(&d_out), total, st_));
-      k_expand<uint8_t><<<grid_for((n + 31) / 32 * 32, 256), 256, 0, st_>>>(d_len, d_src, n, d_tbytes_, d_out);
+      k_expand<uint8_t><<<grid_for((n + 31) / 32 * 32, 256), 256, 0, st_>>>(d_len, d_src, nullptr, nullptr, n, d_tbytes_, d_out);
       CK(cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st_));
       CK(cudaStreamSynchronize(st_));
       CK(cudaGetLastError());
@@ -194,120 +192,124 @@ class CudaEncoder {
     return b ? static_cast<int>(b) : 1;
   }
 
+  // Work buffers belong to the encoder and only ever grow: repeated calls on similar inputs allocate nothing (handing GB-sized
+  // blocks back to the stream-ordered pool between calls made it re-grow, ~90 ms per call at 1 GB).
+  struct Buf { void* p = nullptr; uint64_t cap = 0; };
+  template <typename T>
+  int need(Buf& b, uint64_t bytes, T** out) {
+    if (b.cap < bytes) {
+      if (b.p) { CK(cudaStreamSynchronize(st_)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+      const uint64_t want = (bytes + (bytes >> 3) + (2ull << 20) - 1) & ~((2ull << 20) - 1);  // 12 % slack, 2 MB granules
+      CK(cudaMalloc(&b.p, want));
+      b.cap = want;
+    }
+    *out = static_cast<T*>(b.p);
+    return 0;
+  }
+
   // exclusive scan of a[0, n) in place; a[n] receives the total (a holds n + 1 entries)
-  int scan_in_place(ull* a, uint64_t n, ull** sums_buf) {
+  int scan_in_place(ull* a, uint64_t n) {
     const uint32_t nb = static_cast<uint32_t>((n + SCAN_TILE - 1) / SCAN_TILE);
     if (nb == 0) { CK(cudaMemsetAsync(a, 0, 8, st_)); return 0; }
-    if (*sums_buf) { afree(*sums_buf); *sums_buf = nullptr; }
-    CK(cudaMallocAsync(reinterpret_cast<void**>(sums_buf), static_cast<uint64_t>(nb) * 8, st_));
-    k_scan_sums<<<nb, SCAN_THREADS, 0, st_>>>(a, n, *sums_buf);
-    k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(*sums_buf, nb, a + n);
-    k_scan_apply<<<nb, SCAN_THREADS, 0, st_>>>(a, n, *sums_buf, a);
+    ull* sums = nullptr;
+    RC(need(b_sums_, static_cast<uint64_t>(nb) * 8, &sums));
+    k_scan_sums<<<nb, SCAN_THREADS, 0, st_>>>(a, n, sums);
+    k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(sums, nb, a + n);
+    k_scan_apply<<<nb, SCAN_THREADS, 0, st_>>>(a, n, sums, a);
     launches_ += 3;
     return 0;
   }
 
   int encode_device(const uint8_t* d_text, uint64_t n) {
     WordTable wt; std::memset(&wt, 0, sizeof wt);
-    uint32_t *u_slot = nullptr, *enc_len = nullptr, *u_n = reinterpret_cast<uint32_t*>(scal_);
-    ull *u_len = nullptr, *enc_off = nullptr, *unit_cnt = nullptr, *tok_src = nullptr, *sums = nullptr;
+    uint32_t *u_slot = nullptr, *enc_len = nullptr, *tok_slot = nullptr, *u_n = reinterpret_cast<uint32_t*>(scal_);
+    ull *u_len = nullptr, *enc_off = nullptr, *unit_cnt = nullptr;
     int32_t* pool = nullptr;
-    auto free_wt = [&]() { afree(wt.tag); afree(wt.first); afree(wt.count); afree(wt.len); afree(wt.bucket); std::memset(&wt, 0, sizeof wt); };
-    auto cleanup = [&]() { free_wt(); afree(u_slot); afree(enc_len); afree(u_len); afree(enc_off); afree(unit_cnt);
-                           afree(tok_src); afree(sums); afree(pool); };
-    auto body = [&]() -> int {
-      CK(cudaEventRecord(ev_[0], st_));
-      // --- distinct words of the text (same table and retry rules as the trainer's ingest)
-      DevCounters zero; std::memset(&zero, 0, sizeof zero);
-      DevCounters c;
-      uint64_t cap = next_pow2(n / 64 + 1); if (cap < (1u << 16)) cap = 1u << 16;
-      uint32_t seed = 0x5bd1e995u;
-      for (int attempt = 0;; ++attempt) {
-        if (attempt > 8 || cap > (1ull << 32)) { std::fprintf(stderr, "[ERROR]\t encoder: distinct-word table did not converge\n"); return -1; }
-        CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.tag), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.first), cap * 8, st_));
-        CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.count), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.len), cap * 4, st_));
-        CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.bucket), cap * 4, st_));
-        wt.cap = cap; wt.mask = cap - 1;
-        CK(cudaMemsetAsync(wt.tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt.first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt.count, 0, cap * 8, st_));
-        CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
-        if (n) { k_tokenize<<<grid_for((n + 15) / 16, 256), 256, 0, st_>>>(d_text, n, wt, ctr_, seed); launches_++; }
-        CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
-        CK(cudaStreamSynchronize(st_));
-        CK(cudaGetLastError());
-        const bool too_full = static_cast<uint64_t>(c.n_unique) * 2 > cap;
-        if ((c.err & (ERR_WT_FULL | ERR_WT_COLLISION)) || too_full) {  // NUL bytes are ordinary word content here
-          free_wt();
-          if ((c.err & ERR_WT_FULL) || too_full) cap *= 4;
-          if (c.err & ERR_WT_COLLISION) seed = seed * 2654435761u + 12345u;
-          continue;
-        }
-        break;
-      }
-      const uint32_t N = c.n_unique;
-      n_tok_ = c.n_tokens;
-      stats_.n_unique_words = N;
-      CK(cudaEventRecord(ev_[1], st_));
-
-      // --- every distinct word once
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&u_slot), (static_cast<uint64_t>(N) + 1) * 4, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&u_len), (static_cast<uint64_t>(N) + 1) * 8, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&enc_len), cap * 4, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&enc_off), cap * 8, st_));
-      CK(cudaMemsetAsync(u_n, 0, 4, st_));
-      k_enc_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, u_len); launches_++;
-      RC(scan_in_place(u_len, N, &sums));
-      ull pool_n = 0;
-      CK(cudaMemcpyAsync(&pool_n, u_len + N, 8, cudaMemcpyDeviceToHost, st_));
-      CK(cudaStreamSynchronize(st_));
-      stats_.pool_ids = pool_n;
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&pool), (pool_n + 1) * 4, st_));
-      if (N) { k_enc_words<<<grid_for(static_cast<uint64_t>(N) * 32, ENC_WARPS * 32), ENC_WARPS * 32, 0, st_>>>(d_text, wt, u_slot, u_len, N, mt_, pool, enc_len, enc_off); launches_++; }
-      CK(cudaEventRecord(ev_[2], st_));
-
-      // --- every occurrence, in text order
-      const uint64_t n_units = (n + UNIT_BYTES - 1) / UNIT_BYTES;
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&unit_cnt), (n_units + 1) * 8, st_));
-      if (n_units) { k_enc_count_starts<<<grid_for(n_units * 256, 256), 256, 0, st_>>>(d_text, n, n_units, unit_cnt); launches_++; }
-      RC(scan_in_place(unit_cnt, n_units, &sums));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&d_off_), (n_tok_ + 1) * 8, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&tok_src), (n_tok_ + 1) * 8, st_));
-      have_result_ = true;
-      if (n_units) { k_enc_lookup<<<grid_for(n_units * 256, 256), 256, 0, st_>>>(d_text, n, n_units, unit_cnt, wt, seed, enc_len, enc_off, d_off_, tok_src, ctr_); launches_++; }
-      RC(scan_in_place(d_off_, n_tok_, &sums));
-      ull total_tok = 0, n_ids = 0;
-      CK(cudaMemcpyAsync(&total_tok, unit_cnt + n_units, 8, cudaMemcpyDeviceToHost, st_));
-      CK(cudaMemcpyAsync(&n_ids, d_off_ + n_tok_, 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaEventRecord(ev_[0], st_));
+    // --- occurrences per 4 KB unit -> index of every occurrence in text order
+    const uint64_t n_units = (n + UNIT_BYTES - 1) / UNIT_BYTES;
+    RC(need(b_unit_, (n_units + 1) * 8, &unit_cnt));
+    if (n_units) { k_enc_count_starts<<<grid_for(n_units * 256, 256), 256, 0, st_>>>(d_text, n, n_units, unit_cnt); launches_++; }
+    RC(scan_in_place(unit_cnt, n_units));
+    ull total_tok = 0;
+    CK(cudaMemcpyAsync(&total_tok, unit_cnt + n_units, 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    n_tok_ = total_tok;
+    RC(need(b_tok_slot_, (n_tok_ + 1) * 4, &tok_slot));
+    // --- distinct words of the text (same table and retry rules as the trainer's ingest); every occurrence notes its word
+    DevCounters zero; std::memset(&zero, 0, sizeof zero);
+    DevCounters c;
+    uint64_t cap = next_pow2(n / 64 + 1); if (cap < (1u << 16)) cap = 1u << 16;
+    if (cap < wt_cap_hint_) cap = wt_cap_hint_;  // what the previous call ended with
+    uint32_t seed = 0x5bd1e995u;
+    for (int attempt = 0;; ++attempt) {
+      if (attempt > 8 || cap > (1ull << 32)) { std::fprintf(stderr, "[ERROR]\t encoder: distinct-word table did not converge\n"); return -1; }
+      RC(need(b_wt_tag_, cap * 8, &wt.tag)); RC(need(b_wt_first_, cap * 8, &wt.first));
+      RC(need(b_wt_len_, cap * 4, &wt.len)); RC(need(b_wt_bucket_, cap * 4, &wt.bucket));
+      wt.cap = cap; wt.mask = cap - 1;
+      CK(cudaMemsetAsync(wt.tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt.first, 0xFF, cap * 8, st_));
+      CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
+      if (n_units) { k_enc_tokenize<<<grid_for(n_units * 256, 256), 256, 0, st_>>>(d_text, n, n_units, unit_cnt, wt, ctr_, seed, tok_slot); launches_++; }
       CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
       CK(cudaStreamSynchronize(st_));
-      if (total_tok != n_tok_ || (c.err & ERR_WT_FULL)) { std::fprintf(stderr, "[ERROR]\t encoder: occurrence pass disagrees with the word table (%llu vs %llu words)\n", total_tok, static_cast<ull>(n_tok_)); return -1; }
-      n_ids_ = n_ids;
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&d_ids_), (n_ids_ + 1) * 4, st_));
-      if (n_tok_) { k_expand<int32_t><<<grid_for((n_tok_ + 31) / 32 * 32, 256), 256, 0, st_>>>(d_off_, tok_src, n_tok_, pool, d_ids_); launches_++; }
-      CK(cudaEventRecord(ev_[3], st_));
-      CK(cudaStreamSynchronize(st_));
       CK(cudaGetLastError());
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ev_[0], ev_[1]); stats_.tokenize_ms = ms;
-      cudaEventElapsedTime(&ms, ev_[1], ev_[2]); stats_.words_ms = ms;
-      cudaEventElapsedTime(&ms, ev_[2], ev_[3]); stats_.expand_ms = ms;
-      cudaEventElapsedTime(&ms, ev_[0], ev_[3]); stats_.device_ms = ms;
-      return 0;
-    };
-    const int rc = body();
-    cleanup();
-    return rc;
+      const bool too_full = static_cast<uint64_t>(c.n_unique) * 2 > cap;
+      if ((c.err & (ERR_WT_FULL | ERR_WT_COLLISION)) || too_full) {
+        if ((c.err & ERR_WT_FULL) || too_full) cap *= 4;
+        if (c.err & ERR_WT_COLLISION) seed = seed * 2654435761u + 12345u;
+        continue;
+      }
+      break;
+    }
+    wt_cap_hint_ = cap <= (1ull << 26) ? cap : 0;
+    const uint32_t N = c.n_unique;
+    stats_.n_unique_words = N;
+    CK(cudaEventRecord(ev_[1], st_));
+
+    // --- every distinct word once
+    RC(need(b_u_slot_, (static_cast<uint64_t>(N) + 1) * 4, &u_slot));
+    RC(need(b_u_len_, (static_cast<uint64_t>(N) + 1) * 8, &u_len));
+    RC(need(b_enc_len_, cap * 4, &enc_len));
+    RC(need(b_enc_off_, cap * 8, &enc_off));
+    CK(cudaMemsetAsync(u_n, 0, 4, st_));
+    k_enc_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, u_len); launches_++;
+    RC(scan_in_place(u_len, N));
+    ull pool_n = 0;
+    CK(cudaMemcpyAsync(&pool_n, u_len + N, 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    stats_.pool_ids = pool_n;
+    RC(need(b_pool_, (pool_n + 1) * 4, &pool));
+    if (N) { k_enc_words<<<grid_for(static_cast<uint64_t>(N) * 32, ENC_WARPS * 32), ENC_WARPS * 32, 0, st_>>>(d_text, wt, u_slot, u_len, N, mt_, pool, enc_len, enc_off); launches_++; }
+    CK(cudaEventRecord(ev_[2], st_));
+
+    // --- occurrences copy their word's ids
+    RC(need(b_off_, (n_tok_ + 1) * 8, &d_off_));
+    if (n_tok_) { k_enc_toklen<<<grid_for(n_tok_, 256), 256, 0, st_>>>(tok_slot, n_tok_, enc_len, d_off_); launches_++; }
+    RC(scan_in_place(d_off_, n_tok_));
+    ull n_ids = 0;
+    CK(cudaMemcpyAsync(&n_ids, d_off_ + n_tok_, 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    n_ids_ = n_ids;
+    RC(need(b_ids_, (n_ids_ + 1) * 4, &d_ids_));
+    if (n_tok_) { k_expand<int32_t><<<grid_for((n_tok_ + 31) / 32 * 32, 256), 256, 0, st_>>>(d_off_, nullptr, tok_slot, enc_off, n_tok_, pool, d_ids_); launches_++; }
+    CK(cudaEventRecord(ev_[3], st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[1]); stats_.tokenize_ms = ms;
+    cudaEventElapsedTime(&ms, ev_[1], ev_[2]); stats_.words_ms = ms;
+    cudaEventElapsedTime(&ms, ev_[2], ev_[3]); stats_.expand_ms = ms;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[3]); stats_.device_ms = ms;
+    return 0;
   }
 
-  void drop_result() {
-    if (d_ids_) afree(d_ids_);
-    if (d_off_) afree(d_off_);
-    d_ids_ = nullptr; d_off_ = nullptr; n_ids_ = 0; n_tok_ = 0; have_result_ = false;
-  }
   void release() {
     if (!st_) return;
     cudaSetDevice(dev_);
-    drop_result();
     cudaStreamSynchronize(st_);
+    for (Buf* b : {&b_text_, &b_unit_, &b_sums_, &b_tok_slot_, &b_wt_tag_, &b_wt_first_, &b_wt_len_, &b_wt_bucket_, &b_u_slot_, &b_u_len_, &b_enc_len_, &b_enc_off_,
+                   &b_pool_, &b_off_, &b_ids_})
+      if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     cudaFree(ctr_); cudaFree(d_ent_); cudaFree(d_pair_); cudaFree(d_toff_); cudaFree(d_tbytes_);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(st_);
@@ -323,7 +325,9 @@ class CudaEncoder {
   std::vector<int32_t> tri_;
   MergeEnt* d_ent_ = nullptr; int2* d_pair_ = nullptr; MergeTable mt_{};
   ull* d_toff_ = nullptr; uint8_t* d_tbytes_ = nullptr;
-  int32_t* d_ids_ = nullptr; ull* d_off_ = nullptr;
+  Buf b_text_, b_unit_, b_sums_, b_tok_slot_, b_wt_tag_, b_wt_first_, b_wt_len_, b_wt_bucket_, b_u_slot_, b_u_len_, b_enc_len_, b_enc_off_, b_pool_, b_off_, b_ids_;
+  uint64_t wt_cap_hint_ = 0;
+  int32_t* d_ids_ = nullptr; ull* d_off_ = nullptr;  // views into b_ids_ / b_off_: the last result
   uint64_t n_ids_ = 0, n_tok_ = 0;
   bool have_result_ = false;
   uint64_t launches_ = 0;

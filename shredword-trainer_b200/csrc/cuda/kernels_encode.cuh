@@ -123,10 +123,10 @@ __global__ void __launch_bounds__(256) k_enc_count_starts(const uint8_t* __restr
   }
 }
 
-// every occurrence, in text order: word-table slot of its word -> (encoded length, where its ids are in the pool)
-__global__ void __launch_bounds__(256) k_enc_lookup(const uint8_t* __restrict__ text, uint64_t n, uint64_t n_units, const ull* __restrict__ unit_base,
-                                                    WordTable wt, uint32_t seed, const uint32_t* __restrict__ enc_len, const ull* __restrict__ enc_off,
-                                                    ull* __restrict__ tok_len, ull* __restrict__ tok_src, DevCounters* ctr) {
+// Tokenise for the encoder: every occurrence (in text order; unit_base = occurrences before each 4 KB unit) finds or claims
+// the word-table slot of its word and records it.  Same table as the trainer's k_tokenize, minus the occurrence counts.
+__global__ void __launch_bounds__(256) k_enc_tokenize(const uint8_t* __restrict__ text, uint64_t n, uint64_t n_units, const ull* __restrict__ unit_base,
+                                                      WordTable wt, DevCounters* ctr, uint32_t seed, uint32_t* __restrict__ tok_slot) {
   __shared__ uint32_t ws[8];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -146,33 +146,30 @@ __global__ void __launch_bounds__(256) k_enc_lookup(const uint8_t* __restrict__ 
       starts &= starts - 1;
       uint32_t len, dj;
       const uint64_t tag = token_walk(text, base + i, seed, &len, &dj);
-      uint64_t slot = tag & wt.mask;
-      bool found = false;
-      for (uint32_t probe = 0; probe < 8192u; ++probe) {
-        const ull cur = wt.tag[slot];
-        if (cur == tag) { found = true; break; }
-        if (cur == 0ull) break;
-        slot = (slot + 1) & wt.mask;
-      }
-      if (!found) { atomicOr(&ctr->err, ERR_WT_FULL); tok_len[t] = 0; tok_src[t] = 0; }
-      else { tok_len[t] = enc_len[slot]; tok_src[t] = enc_off[slot]; }
-      ++t;
+      tok_slot[t++] = static_cast<uint32_t>(word_insert<false>(text, wt, ctr, base + i, tag, len, dj));
     }
   }
 }
 
+// encoded length of every occurrence (scanned into the CSR offsets of the output afterwards)
+__global__ void k_enc_toklen(const uint32_t* __restrict__ tok_slot, uint64_t n_tok, const uint32_t* __restrict__ enc_len, ull* __restrict__ tok_len) {
+  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n_tok; t += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    tok_len[t] = enc_len[tok_slot[t]];
+}
+
 // One warp per 32 consecutive items (word occurrences when encoding, token ids when decoding): item i owns out[off[i], off[i+1])
-// and copies it from src_pool[src[i] ...].  Lanes walk the OUTPUT positions, so stores are fully coalesced; the owning item of
-// a position is found by a 5-step binary search over the 32 offsets held in the lanes.
+// and copies it from src_pool[src ...], src = src_of[i] (decode) or slot_src[slot_of[i]] (encode: the word's place in the pool).
+// Lanes walk the OUTPUT positions, so stores are fully coalesced; the owning item of a position is found by a 5-step binary
+// search over the 32 offsets held in the lanes.
 template <typename T>
-__global__ void __launch_bounds__(256) k_expand(const ull* __restrict__ off, const ull* __restrict__ src, uint64_t n_items, const T* __restrict__ src_pool,
-                                                T* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_expand(const ull* __restrict__ off, const ull* __restrict__ src_of, const uint32_t* __restrict__ slot_of,
+                                                const ull* __restrict__ slot_src, uint64_t n_items, const T* __restrict__ src_pool, T* __restrict__ out) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t n_warps = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
   for (uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; i0 < n_items; i0 += n_warps * 32u) {
     const uint64_t i = i0 + lane;
     const ull my_off = off[i < n_items ? i : n_items];
-    const ull my_src = i < n_items ? src[i] : 0ull;
+    const ull my_src = i < n_items ? (slot_of ? slot_src[slot_of[i]] : src_of[i]) : 0ull;
     const ull first = __shfl_sync(0xFFFFFFFFu, my_off, 0);
     const uint64_t last_item = i0 + 32 < n_items ? i0 + 32 : n_items;
     const uint32_t total = static_cast<uint32_t>(off[last_item] - first);

@@ -36,6 +36,46 @@ __device__ __forceinline__ uint32_t start_mask16(const uint4& v, uint32_t prev) 
   return ~dm & ((dm << 1) | (is_delim(prev) ? 1u : 0u)) & 0xFFFFu;
 }
 
+// Find or claim the word-table slot of the token at `off` (tag, len, dj from token_walk): first offset by look-then-atomicMin,
+// occurrence count (COUNT; the encoder does not need it), and a byte comparison with the word's representative -- two
+// words with the same 64-bit tag raise ERR_WT_COLLISION and the caller starts over with another seed.  Returns the slot.
+template <bool COUNT>
+__device__ __forceinline__ uint64_t word_insert(const uint8_t* __restrict__ text, const WordTable& wt, DevCounters* ctr, uint64_t off, uint64_t tag, uint32_t len,
+                                                uint32_t dj) {
+  uint64_t slot = tag & wt.mask;
+  for (uint32_t probe = 0; probe < 8192u; ++probe) {
+    ull cur = wt.tag[slot];
+    if (cur == 0ull) {
+      ull prevt = atomicCAS(&wt.tag[slot], 0ull, static_cast<ull>(tag));
+      if (prevt == 0ull) {  // claimed: publish the immutable facts
+        wt.len[slot] = len;
+        wt.bucket[slot] = dj & 4095u;
+        atomicAdd(&ctr->n_unique, 1u);
+        cur = tag;
+      } else cur = prevt;
+    }
+    if (cur == tag) {
+      // first occurrence: most tokens come after the word's first sighting, so look before paying for an atomic
+      ull old = *reinterpret_cast<volatile ull*>(&wt.first[slot]);
+      if (off < old) old = atomicMin(&wt.first[slot], static_cast<ull>(off));
+      if (COUNT) {  // lanes of this warp that hit the same slot right now add once (hot words are most of a Zipf corpus)
+        const unsigned am = __activemask();
+        const unsigned grp = __match_any_sync(am, slot);
+        if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(grp) - 1)) atomicAdd(&wt.count[slot], static_cast<ull>(__popc(grp)));
+      }
+      if (old != SEQ_MAX && old != off) {  // same tag: must be the same bytes
+        bool same = is_delim(text[old + len]);
+        for (uint32_t j = 0; j < len && same; j++) same = text[old + j] == text[off + j];
+        if (!same) atomicOr(&ctr->err, ERR_WT_COLLISION);
+      }
+      return slot;
+    }
+    slot = (slot + 1) & wt.mask;
+  }
+  atomicOr(&ctr->err, ERR_WT_FULL);
+  return ~0ull;
+}
+
 // Each thread owns 16 consecutive corpus bytes (one uint4 load) and inserts every token that STARTS inside them.
 // text is padded with >= 32 spaces, so token walks terminate.
 __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
@@ -59,37 +99,7 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ te
       uint32_t len, dj;
       const uint64_t tag = token_walk(text, off, seed, &len, &dj);
       ++my_tokens;
-      uint64_t slot = tag & wt.mask;
-      bool done = false;
-      for (uint32_t probe = 0; probe < 8192u && !done; ++probe) {
-        ull cur = wt.tag[slot];
-        if (cur == 0ull) {
-          ull prevt = atomicCAS(&wt.tag[slot], 0ull, static_cast<ull>(tag));
-          if (prevt == 0ull) {  // claimed: publish the immutable facts
-            wt.len[slot] = len;
-            wt.bucket[slot] = dj & 4095u;
-            atomicAdd(&ctr->n_unique, 1u);
-            cur = tag;
-          } else cur = prevt;
-        }
-        if (cur == tag) {
-          // first occurrence: most tokens come after the word's first sighting, so look before paying for an atomic
-          ull old = *reinterpret_cast<volatile ull*>(&wt.first[slot]);
-          if (off < old) old = atomicMin(&wt.first[slot], static_cast<ull>(off));
-          {  // count: lanes of this warp that hit the same slot right now add once (hot words are most of a Zipf corpus)
-            const unsigned am = __activemask();
-            const unsigned grp = __match_any_sync(am, slot);
-            if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(grp) - 1)) atomicAdd(&wt.count[slot], static_cast<ull>(__popc(grp)));
-          }
-          if (old != SEQ_MAX && old != off) {  // same tag: must be the same bytes, else retry ingest with a new seed
-            bool same = is_delim(text[old + len]);
-            for (uint32_t j = 0; j < len && same; j++) same = text[old + j] == text[off + j];
-            if (!same) atomicOr(&ctr->err, ERR_WT_COLLISION);
-          }
-          done = true;
-        } else slot = (slot + 1) & wt.mask;
-      }
-      if (!done) atomicOr(&ctr->err, ERR_WT_FULL);
+      word_insert<true>(text, wt, ctr, off, tag, len, dj);
     }
   }
   // token count: warp reduce, one atomic per warp

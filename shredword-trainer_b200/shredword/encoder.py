@@ -62,6 +62,18 @@ class BPEEncoder:
             raise RuntimeError("bpe_b200_encode_fetch failed")
         return ids, off
 
+    def encode_raw(self, ptr, n_bytes):
+        """encode n_bytes at host address ptr; results stay on the device -> (n_words, n_ids)"""
+        n_words, n_ids = ctypes.c_uint64(), ctypes.c_uint64()
+        if lib.bpe_b200_encode(self._need(), ptr, n_bytes, ctypes.byref(n_words), ctypes.byref(n_ids)) != 0:
+            raise RuntimeError("bpe_b200_encode failed")
+        return n_words.value, n_ids.value
+
+    def fetch_raw(self, ids_ptr, offsets_ptr):
+        """copy the last result to host addresses (int32[n_ids], uint64[n_words + 1]; either may be None)"""
+        if lib.bpe_b200_encode_fetch(self._need(), ids_ptr, offsets_ptr) != 0:
+            raise RuntimeError("bpe_b200_encode_fetch failed")
+
     def encode(self, text):
         """reference BPETokenizer.encode (utils/bpe.py:205-212): text -> list of token ids"""
         data = text.encode("utf-8") if isinstance(text, str) else text
