@@ -71,19 +71,15 @@ class CudaEncoder {
     tri_.assign(tri, tri + 3 * n);
     const uint64_t cap = next_pow2(4 * n + 16);
     std::vector<MergeEnt> ent(cap, MergeEnt{0, 0, 0});
-    std::vector<int2> pair(n + 1);
     for (size_t m = 0; m < n; m++) {
       const uint64_t k = ((static_cast<uint64_t>(static_cast<uint32_t>(tri[3 * m])) << 32) | static_cast<uint32_t>(tri[3 * m + 1])) + 1ull;
       uint64_t s = mix64(k) & (cap - 1);
       while (ent[s].key != 0 && ent[s].key != k) s = (s + 1) & (cap - 1);
       ent[s].key = k; ent[s].val = tri[3 * m + 2];
-      pair[m] = make_int2(tri[3 * m], tri[3 * m + 1]);
     }
     CK(cudaMalloc(reinterpret_cast<void**>(&d_ent_), cap * sizeof(MergeEnt)));
-    CK(cudaMalloc(reinterpret_cast<void**>(&d_pair_), (n + 1) * sizeof(int2)));
     CK(cudaMemcpy(d_ent_, ent.data(), cap * sizeof(MergeEnt), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_pair_, pair.data(), (n + 1) * sizeof(int2), cudaMemcpyHostToDevice));
-    mt_.ent = d_ent_; mt_.pair = d_pair_; mt_.mask = cap - 1;
+    mt_.ent = d_ent_; mt_.mask = cap - 1;
 
     // token bytes: vocab[256 + m] = vocab[a] + vocab[b] (build_vocab, utils/bpe.py:74-76)
     const size_t T = 256 + n;
@@ -310,7 +306,7 @@ class CudaEncoder {
     for (Buf* b : {&b_text_, &b_unit_, &b_sums_, &b_tok_slot_, &b_wt_tag_, &b_wt_first_, &b_wt_len_, &b_wt_bucket_, &b_u_slot_, &b_u_len_, &b_enc_len_, &b_enc_off_,
                    &b_pool_, &b_off_, &b_ids_})
       if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
-    cudaFree(ctr_); cudaFree(d_ent_); cudaFree(d_pair_); cudaFree(d_toff_); cudaFree(d_tbytes_);
+    cudaFree(ctr_); cudaFree(d_ent_); cudaFree(d_toff_); cudaFree(d_tbytes_);
     for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(st_);
     st_ = nullptr;
@@ -323,7 +319,7 @@ class CudaEncoder {
   ull* scal_ = nullptr;
   size_t n_merges_ = 0;
   std::vector<int32_t> tri_;
-  MergeEnt* d_ent_ = nullptr; int2* d_pair_ = nullptr; MergeTable mt_{};
+  MergeEnt* d_ent_ = nullptr; MergeTable mt_{};
   ull* d_toff_ = nullptr; uint8_t* d_tbytes_ = nullptr;
   Buf b_text_, b_unit_, b_sums_, b_tok_slot_, b_wt_tag_, b_wt_first_, b_wt_len_, b_wt_bucket_, b_u_slot_, b_u_len_, b_enc_len_, b_enc_off_, b_pool_, b_off_, b_ids_;
   uint64_t wt_cap_hint_ = 0;

@@ -10,7 +10,6 @@
 struct MergeEnt { uint64_t key; int32_t val; int32_t pad; };  // key = (a << 32 | b) + 1, 0 = empty; one 16-byte load
 struct MergeTable {
   const MergeEnt* ent;   // open addressing, load <= 1/4
-  const int2* pair;      // pair[id - 256] = (a, b) of the row that defines id
   uint64_t mask;
 };
 constexpr int32_t NO_MERGE = 0x7FFFFFFF;
@@ -59,11 +58,21 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_words(const uint8_t* __r
     __syncwarp();
     uint32_t n = len;
     while (n >= 2) {
-      int32_t best = NO_MERGE;
-      for (uint32_t p = lane; p + 1 < n; p += 32) { const int32_t r = merge_lookup(mt, w[p], w[p + 1]); best = r < best ? r : best; }
+      int32_t mine = NO_MERGE;
+      int2 ab = make_int2(-1, -1);  // the pair behind `mine`
+      for (uint32_t p = lane; p + 1 < n; p += 32) {
+        const int32_t x = w[p], y = w[p + 1];
+        const int32_t r = merge_lookup(mt, x, y);
+        if (r < mine) { mine = r; ab = make_int2(x, y); }
+      }
+      int32_t best = mine;
       for (int o = 16; o; o >>= 1) { const int32_t y = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = y < best ? y : best; }
       if (best == NO_MERGE) break;
-      const int2 ab = __ldg(&mt.pair[best - 256]);
+      {  // a merge id belongs to exactly one pair: take it from any lane that found it
+        const int src = __ffs(__ballot_sync(0xFFFFFFFFu, mine == best)) - 1;
+        ab.x = __shfl_sync(0xFFFFFFFFu, ab.x, src);
+        ab.y = __shfl_sync(0xFFFFFFFFu, ab.y, src);
+      }
       uint32_t out = 0, carry = 0, prev_taken = 0;
       for (uint32_t c = 0; c < n; c += 32) {
         const uint32_t p = c + lane;
