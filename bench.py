@@ -158,14 +158,37 @@ def encoder_leg(host, size, merges, peak_hint=None, with_cpu=True, reps=3):
         sts.append(enc.stats())
     wall = sum(walls) / reps
     st = {k: sum(x[k] for x in sts) / reps for k in sts[0]}
+    # streamed entry point: same buffers, H2D | encode | D2H overlapped piece by piece
+    swalls = []
+    for i in range(2 + reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sw_, si_ = enc.encode_to_host_raw(host.data_ptr(), size, ids.data_ptr(), ids.numel(), off.data_ptr(), off.numel())
+        if i >= 2:
+            swalls.append(time.perf_counter() - t0)
+    assert (sw_, si_) == (n_words, n_ids)
+    swall = sum(swalls) / reps
+    sst = enc.stats()
+    iwalls = []                                      # ids only (what the reference's encode() returns): no offsets come back
+    for i in range(1 + reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enc.encode_to_host_raw(host.data_ptr(), size, ids.data_ptr(), ids.numel(), None, 0)
+        if i >= 1:
+            iwalls.append(time.perf_counter() - t0)
+    iwall = sum(iwalls) / reps
     # occurrence phase (count starts + lookup + scans + expand): text read, ids and offsets written
     expand_bytes = size + 4.0 * n_ids + 8.0 * (n_words + 1)
     out = {"what": "bpe_b200_encode + bpe_b200_encode_fetch on the whole bench corpus with the merges of the last timed step; 3 warm-ups, mean of %d runs" % reps,
            "text_bytes": size, "n_words": n_words, "n_unique_words": int(st["n_unique_words"]), "n_ids": n_ids, "ids_per_word": n_ids / max(n_words, 1),
-           "e2e_words_per_s": n_words / wall, "e2e_text_gbs": size / wall / 1e9, "e2e_s": wall,
+           "e2e_words_per_s": n_words / swall, "e2e_text_gbs": size / swall / 1e9, "e2e_s": swall, "e2e_s_runs": [round(x, 5) for x in swalls],
+           "e2e_what": "bpe_b200_encode_to_host (streamed: pieces of 64 MB, H2D | encode | D2H overlapped), pinned host text in, pinned host ids + offsets out",
+           "e2e_streamed_device_ms_sum_of_pieces": sst["device_ms"], "e2e_streamed_launches": int(sst["kernel_launches"]),
+           "e2e_ids_only_s": iwall, "e2e_ids_only_words_per_s": n_words / iwall, "e2e_ids_only_text_gbs": size / iwall / 1e9, "e2e_ids_only_d2h_bytes": 4 * n_ids,
+           "unstreamed_e2e_words_per_s": n_words / wall, "unstreamed_e2e_text_gbs": size / wall / 1e9, "unstreamed_e2e_s": wall,
            "h2d_bytes": size, "d2h_bytes": 4 * n_ids + 8 * (n_words + 1),
            "device_words_per_s": n_words / (st["device_ms"] * 1e-3), "device_text_gbs": size / (st["device_ms"] * 1e-3) / 1e9,
-           "device_ms": st["device_ms"], "device_ms_runs": [round(x["device_ms"], 3) for x in sts], "e2e_s_runs": [round(x, 5) for x in walls], "tokenize_ms": st["tokenize_ms"], "words_ms": st["words_ms"], "expand_ms": st["expand_ms"],
+           "device_ms": st["device_ms"], "device_ms_runs": [round(x["device_ms"], 3) for x in sts], "unstreamed_e2e_s_runs": [round(x, 5) for x in walls], "tokenize_ms": st["tokenize_ms"], "words_ms": st["words_ms"], "expand_ms": st["expand_ms"],
            "h2d_ms": st["h2d_ms"], "d2h_ms": st["d2h_ms"], "kernel_launches": int(st["kernel_launches"]),
            "expand_algorithmic_bytes": expand_bytes, "expand_algorithmic_gbs": expand_bytes / (st["expand_ms"] * 1e-3) / 1e9 if st["expand_ms"] else None}
     if with_cpu:

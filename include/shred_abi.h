@@ -155,6 +155,13 @@ SHRED_API size_t bpe_b200_encoder_vocab_size(const shred_encoder_t* enc);
 SHRED_API int bpe_b200_encode(shred_encoder_t* enc, const uint8_t* text, uint64_t n_bytes, uint64_t* n_words, uint64_t* n_ids);
 /* Copies the last result out: ids_out[n_ids], offsets_out[n_words + 1] (either may be NULL).  0 / -1. */
 SHRED_API int bpe_b200_encode_fetch(shred_encoder_t* enc, int32_t* ids_out, uint64_t* offsets_out);
+/* Streamed encode straight into host buffers (pinned for full speed): the text is cut at delimiters into pieces and piece k + 1
+ * travels to the device while piece k is encoded and piece k - 1 travels back.  Same ids and (global) offsets as
+ * bpe_b200_encode + _fetch.  ids_cap >= n_bytes and offsets_cap >= n_bytes / 2 + 2 always suffice; offsets_out may be NULL
+ * (ids only, like the reference's encode(): 40 % fewer bytes come back).
+ * 0 ok, -1 device error / NULL, -3 a capacity is too small. */
+SHRED_API int bpe_b200_encode_to_host(shred_encoder_t* enc, const uint8_t* text, uint64_t n_bytes, int32_t* ids_out, uint64_t ids_cap,
+                                      uint64_t* offsets_out, uint64_t offsets_cap, uint64_t* n_words, uint64_t* n_ids);
 /* Bytes of the ids back to back into out[cap].  Returns the byte count (nothing written if > cap), -2 for an id outside
  * [0, vocab_size), -1 on a device error. */
 SHRED_API int64_t bpe_b200_decode(shred_encoder_t* enc, const int32_t* ids, uint64_t n_ids, uint8_t* out, uint64_t cap);

@@ -24,15 +24,9 @@ __device__ __forceinline__ int32_t merge_lookup(const MergeTable& mt, int32_t a,
   }
 }
 
-// distinct words -> dense list (arbitrary order) with their byte lengths (= upper bound of their encoded lengths)
-__global__ void k_enc_collect(WordTable wt, uint32_t* u_slot, uint32_t* u_n, ull* u_len) {
-  for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < wt.cap; s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    if (wt.tag[s] != 0ull) {
-      const uint32_t idx = atomicAdd(u_n, 1u);
-      u_slot[idx] = static_cast<uint32_t>(s);
-      u_len[idx] = wt.len[s];
-    }
-  }
+// byte lengths of the words claimed by the last k_enc_tokenize (= upper bounds of their encoded lengths), for the pool offsets
+__global__ void k_enc_newlens(WordTable wt, const uint32_t* __restrict__ new_list, uint32_t n_new, ull* __restrict__ u_len) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) u_len[i] = wt.len[new_list[i]];
 }
 
 // One warp per distinct word.  The ids live in shared memory (words up to ENC_SM_WORD symbols) or in the word's own range of
@@ -44,7 +38,7 @@ constexpr uint32_t ENC_SM_WORD = 128, ENC_WARPS = 8;
 
 __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_words(const uint8_t* __restrict__ text, WordTable wt, const uint32_t* __restrict__ u_slot,
                                                                const ull* __restrict__ u_off, uint32_t n_unique, MergeTable mt, int32_t* __restrict__ pool,
-                                                               uint32_t* __restrict__ enc_len, ull* __restrict__ enc_off) {
+                                                               ull pool_base, uint32_t* __restrict__ enc_len, ull* __restrict__ enc_off) {
   __shared__ int32_t sm[ENC_WARPS][ENC_SM_WORD];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -52,7 +46,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_words(const uint8_t* __r
   for (uint32_t u = blockIdx.x * ENC_WARPS + warp; u < n_unique; u += n_warps) {
     const uint32_t slot = u_slot[u];
     const uint32_t len = wt.len[slot];
-    const ull first = wt.first[slot], base = u_off[u];
+    const ull first = wt.first[slot], base = pool_base + u_off[u];
     int32_t* w = len <= ENC_SM_WORD ? sm[warp] : pool + base;
     for (uint32_t p = lane; p < len; p += 32) w[p] = text[first + p];
     __syncwarp();
@@ -106,24 +100,27 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_words(const uint8_t* __r
   }
 }
 
-// ---- occurrences.  A "unit" is the 4096 corpus bytes one 256-thread block handles per step (16 bytes per thread).
+// ---- occurrences.  A "unit" is the 4096 corpus bytes one 256-thread block handles per step (16 bytes per thread); units are
+// aligned in the whole text, a call works on the occurrences that START in the window [lo, hi) (one piece of the text).
 constexpr uint32_t UNIT_BYTES = 4096;
 
-__device__ __forceinline__ uint32_t unit_starts(const uint8_t* __restrict__ text, uint64_t n, uint64_t unit, uint64_t* base_out) {
+__device__ __forceinline__ uint32_t unit_starts(const uint8_t* __restrict__ text, uint64_t lo, uint64_t hi, uint64_t unit, uint64_t* base_out) {
   const uint64_t base = unit * UNIT_BYTES + static_cast<uint64_t>(threadIdx.x) * 16u;
   *base_out = base;
-  if (base >= n) return 0;
+  if (base >= hi || base + 16 <= lo) return 0;
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
   uint32_t starts = start_mask16(v, base ? text[base - 1] : 32u);
-  if (base + 16 > n) starts &= (1u << (n - base)) - 1u;
+  if (base + 16 > hi) starts &= (1u << (hi - base)) - 1u;
+  if (base < lo) starts &= ~((1u << (lo - base)) - 1u);
   return starts;
 }
 
-__global__ void __launch_bounds__(256) k_enc_count_starts(const uint8_t* __restrict__ text, uint64_t n, uint64_t n_units, ull* __restrict__ unit_cnt) {
+__global__ void __launch_bounds__(256) k_enc_count_starts(const uint8_t* __restrict__ text, uint64_t lo, uint64_t hi, uint64_t u0, uint64_t n_units,
+                                                          ull* __restrict__ unit_cnt) {
   __shared__ uint32_t ws[8];
   for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     uint64_t base;
-    uint32_t c = __popc(unit_starts(text, n, unit, &base));
+    uint32_t c = __popc(unit_starts(text, lo, hi, u0 + unit, &base));
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if ((threadIdx.x & 31u) == 0) ws[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -132,15 +129,18 @@ __global__ void __launch_bounds__(256) k_enc_count_starts(const uint8_t* __restr
   }
 }
 
-// Tokenise for the encoder: every occurrence (in text order; unit_base = occurrences before each 4 KB unit) finds or claims
-// the word-table slot of its word and records it.  Same table as the trainer's k_tokenize, minus the occurrence counts.
-__global__ void __launch_bounds__(256) k_enc_tokenize(const uint8_t* __restrict__ text, uint64_t n, uint64_t n_units, const ull* __restrict__ unit_base,
-                                                      WordTable wt, DevCounters* ctr, uint32_t seed, uint32_t* __restrict__ tok_slot) {
+// Tokenise for the encoder: every occurrence of the window (in text order; unit_base = occurrences before each unit) finds or
+// claims the word-table slot of its word and records it; newly claimed words are listed.  Same table as the trainer's
+// k_tokenize, minus the occurrence counts.  The table persists across the pieces of one call.
+__global__ void __launch_bounds__(256) k_enc_tokenize(const uint8_t* __restrict__ text, uint64_t lo, uint64_t hi, uint64_t u0, uint64_t n_units,
+                                                      const ull* __restrict__ unit_base, WordTable wt, DevCounters* ctr, uint32_t seed, uint32_t* __restrict__ tok_slot,
+                                                      uint32_t* __restrict__ new_list, uint32_t* __restrict__ new_n) {
   __shared__ uint32_t ws[8];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t my_claims = 0;
   for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     uint64_t base;
-    uint32_t starts = unit_starts(text, n, unit, &base);
+    uint32_t starts = unit_starts(text, lo, hi, u0 + unit, &base);
     const uint32_t c = __popc(starts);
     uint32_t incl = c;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += y; }
@@ -155,9 +155,11 @@ __global__ void __launch_bounds__(256) k_enc_tokenize(const uint8_t* __restrict_
       starts &= starts - 1;
       uint32_t len, dj;
       const uint64_t tag = token_walk(text, base + i, seed, &len, &dj);
-      tok_slot[t++] = static_cast<uint32_t>(word_insert<false>(text, wt, ctr, base + i, tag, len, dj));
+      tok_slot[t++] = static_cast<uint32_t>(word_insert<false, true>(text, wt, ctr, base + i, tag, len, dj, &my_claims, new_list, new_n));
     }
   }
+  for (int o = 16; o; o >>= 1) my_claims += __shfl_down_sync(0xFFFFFFFFu, my_claims, o);
+  if (lane == 0 && my_claims) atomicAdd(&ctr->n_unique, my_claims);
 }
 
 // encoded length of every occurrence (scanned into the CSR offsets of the output afterwards)
@@ -197,6 +199,18 @@ __global__ void __launch_bounds__(256) k_expand(const ull* __restrict__ off, con
       if (j < total) out[first + j] = src_pool[s0 + (j - r0)];
     }
   }
+}
+
+// Small results the host needs between launches go to mapped pinned memory: a copy-engine readback would queue behind the
+// result copy of the previous piece (2 ms at 64 MB pieces).
+__global__ void k_mirror(const ull* __restrict__ src, volatile ull* dst_mapped, uint32_t n_words) {
+  for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst_mapped[i] = src[i];
+  __threadfence_system();
+}
+
+// streamed encode: the CSR offsets of a piece become global
+__global__ void k_add_u64(ull* __restrict__ a, uint64_t n, ull base) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) a[i] += base;
 }
 
 // decode: byte length and source of every id; an id outside [0, vocab) raises the error flag

@@ -39,9 +39,11 @@ __device__ __forceinline__ uint32_t start_mask16(const uint4& v, uint32_t prev) 
 // Find or claim the word-table slot of the token at `off` (tag, len, dj from token_walk): first offset by look-then-atomicMin,
 // occurrence count (COUNT; the encoder does not need it), and a byte comparison with the word's representative -- two
 // words with the same 64-bit tag raise ERR_WT_COLLISION and the caller starts over with another seed.  Returns the slot.
-template <bool COUNT>
+// Claims are counted in the caller's register (*n_claimed; one atomic per warp at the end of the kernel instead of one per
+// new word on a single address); LIST appends the claimed slot to new_list (one atomic per converged group of claimers).
+template <bool COUNT, bool LIST>
 __device__ __forceinline__ uint64_t word_insert(const uint8_t* __restrict__ text, const WordTable& wt, DevCounters* ctr, uint64_t off, uint64_t tag, uint32_t len,
-                                                uint32_t dj) {
+                                                uint32_t dj, uint32_t* n_claimed, uint32_t* new_list = nullptr, uint32_t* new_n = nullptr) {
   uint64_t slot = tag & wt.mask;
   for (uint32_t probe = 0; probe < 8192u; ++probe) {
     ull cur = wt.tag[slot];
@@ -50,7 +52,16 @@ __device__ __forceinline__ uint64_t word_insert(const uint8_t* __restrict__ text
       if (prevt == 0ull) {  // claimed: publish the immutable facts
         wt.len[slot] = len;
         wt.bucket[slot] = dj & 4095u;
-        atomicAdd(&ctr->n_unique, 1u);
+        ++*n_claimed;
+        if (LIST) {
+          const unsigned grp = __activemask();
+          const unsigned lane = threadIdx.x & 31u;
+          const int leader = __ffs(grp) - 1;
+          uint32_t at = 0;
+          if (lane == static_cast<unsigned>(leader)) at = atomicAdd(new_n, static_cast<uint32_t>(__popc(grp)));
+          at = __shfl_sync(grp, at, leader);
+          new_list[at + __popc(grp & ((1u << lane) - 1u))] = static_cast<uint32_t>(slot);
+        }
         cur = tag;
       } else cur = prevt;
     }
@@ -80,7 +91,7 @@ __device__ __forceinline__ uint64_t word_insert(const uint8_t* __restrict__ text
 // text is padded with >= 32 spaces, so token walks terminate.
 __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
   const uint64_t n16 = (n + 15) >> 4;
-  uint32_t my_tokens = 0;
+  uint32_t my_tokens = 0, my_claims = 0;
   for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n16; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t base = t << 4;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
@@ -99,10 +110,11 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ te
       uint32_t len, dj;
       const uint64_t tag = token_walk(text, off, seed, &len, &dj);
       ++my_tokens;
-      word_insert<true>(text, wt, ctr, off, tag, len, dj);
+      word_insert<true, false>(text, wt, ctr, off, tag, len, dj, &my_claims);
     }
   }
-  // token count: warp reduce, one atomic per warp
-  for (int o = 16; o; o >>= 1) my_tokens += __shfl_down_sync(0xFFFFFFFFu, my_tokens, o);
+  // token and new-word counts: warp reduce, one atomic per warp
+  for (int o = 16; o; o >>= 1) { my_tokens += __shfl_down_sync(0xFFFFFFFFu, my_tokens, o); my_claims += __shfl_down_sync(0xFFFFFFFFu, my_claims, o); }
   if ((threadIdx.x & 31) == 0 && my_tokens) atomicAdd(&ctr->n_tokens, static_cast<ull>(my_tokens));
+  if ((threadIdx.x & 31) == 0 && my_claims) atomicAdd(&ctr->n_unique, my_claims);
 }

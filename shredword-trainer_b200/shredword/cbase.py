@@ -107,6 +107,7 @@ lib.bpe_b200_encoder_load.argtypes, lib.bpe_b200_encoder_load.restype = [c_char_
 lib.bpe_b200_encoder_destroy.argtypes, lib.bpe_b200_encoder_destroy.restype = [c_void_p], None
 lib.bpe_b200_encoder_vocab_size.argtypes, lib.bpe_b200_encoder_vocab_size.restype = [c_void_p], c_size_t
 lib.bpe_b200_encode.argtypes, lib.bpe_b200_encode.restype = [c_void_p, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)], c_int
+lib.bpe_b200_encode_to_host.argtypes, lib.bpe_b200_encode_to_host.restype = [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64)], c_int
 lib.bpe_b200_encode_fetch.argtypes, lib.bpe_b200_encode_fetch.restype = [c_void_p, c_void_p, c_void_p], c_int
 lib.bpe_b200_decode.argtypes, lib.bpe_b200_decode.restype = [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64], c_int64
 lib.bpe_b200_encoder_get_stats.argtypes, lib.bpe_b200_encoder_get_stats.restype = [c_void_p, POINTER(EncodeStats)], c_int

@@ -74,6 +74,28 @@ class BPEEncoder:
         if lib.bpe_b200_encode_fetch(self._need(), ids_ptr, offsets_ptr) != 0:
             raise RuntimeError("bpe_b200_encode_fetch failed")
 
+    def encode_to_host_raw(self, ptr, n_bytes, ids_ptr, ids_cap, offsets_ptr, offsets_cap):
+        """streamed encode (H2D | encode | D2H overlapped) from host address ptr into host buffers -> (n_words, n_ids)"""
+        n_words, n_ids = ctypes.c_uint64(), ctypes.c_uint64()
+        rc = lib.bpe_b200_encode_to_host(self._need(), ptr, n_bytes, ids_ptr, ids_cap, offsets_ptr, offsets_cap, ctypes.byref(n_words), ctypes.byref(n_ids))
+        if rc == -3:
+            raise ValueError("output buffers too small")
+        if rc != 0:
+            raise RuntimeError("bpe_b200_encode_to_host failed")
+        return n_words.value, n_ids.value
+
+    def encode_bytes_streamed(self, data):
+        """same result as encode_bytes through the streamed entry point (worst-case sized outputs)"""
+        if isinstance(data, np.ndarray):
+            buf, n = data.ctypes.data, data.nbytes
+        else:
+            data = bytes(data) if not isinstance(data, bytes) else data
+            buf, n = ctypes.cast(ctypes.c_char_p(data), ctypes.c_void_p), len(data)
+        ids = np.empty(max(n, 1), dtype=np.int32)
+        off = np.empty(n // 2 + 2, dtype=np.uint64)
+        n_words, n_ids = self.encode_to_host_raw(buf, n, ids.ctypes.data, ids.size, off.ctypes.data, off.size)
+        return ids[:n_ids], off[:n_words + 1]
+
     def encode(self, text):
         """reference BPETokenizer.encode (utils/bpe.py:205-212): text -> list of token ids"""
         data = text.encode("utf-8") if isinstance(text, str) else text

@@ -173,3 +173,39 @@ def test_encoding_the_training_corpus_reproduces_the_trainers_words_at_scale(E, 
         assert sid[int(soff[k]):int(soff[k + 1])].tolist() == words[i][0], i
     for x in (t, e, o, o2):
         x.destroy()
+
+
+@pytest.mark.parametrize("piece", [1, 7, 64, 4096, 1 << 20])
+def test_streamed_encode_equals_resident_encode(piece, E, monkeypatch):
+    """bpe_b200_encode_to_host cuts the text at delimiters into pieces and overlaps H2D | encode | D2H; ids and (global)
+    offsets must not depend on the cut.  Tiny pieces put a cut after nearly every word."""
+    monkeypatch.setenv("SHRED_ENCODE_PIECE_BYTES", str(piece))
+    for mname, tnames in (("kat_py_300", ["kat_py", "crlf_tabs", "empty", "delims_only", "one_byte", "all_bytes", "no_trailing"]),
+                          ("zipf2m_1000", ["zipf2m", "long_words", "kat_cpp"]), ("handmade_dup", ["runs", "rnd005"])):
+        e, o = E(merges=MODELS[mname]), EncodeOracle(MODELS[mname])
+        for tname in tnames:
+            data = text_bytes(tname)
+            if piece < 64 and len(data) > 200_000:
+                data = data[:200_000]
+            ids, off = e.encode_bytes_streamed(data)
+            oi, oo = o.encode_bytes(data)
+            assert ids.tobytes() == oi and off.tobytes() == oo, (mname, tname)
+            st = e.stats()
+            assert st["n_words"] == off.size - 1 and st["n_ids"] == ids.size
+        # capacities: exact fit works, one short fails with -3 (ValueError)
+        data = text_bytes("kat_cpp")
+        ids, off = e.encode_bytes_streamed(data)
+        a = np.empty(ids.size, dtype=np.int32); b = np.empty(off.size, dtype=np.uint64)
+        buf = np.frombuffer(data, dtype=np.uint8)
+        assert e.encode_to_host_raw(buf.ctypes.data, buf.size, a.ctypes.data, a.size, b.ctypes.data, b.size) == (off.size - 1, ids.size)
+        assert np.array_equal(a, ids) and np.array_equal(b, off)
+        with pytest.raises(ValueError):
+            e.encode_to_host_raw(buf.ctypes.data, buf.size, a.ctypes.data, a.size - 1, b.ctypes.data, b.size)
+        with pytest.raises(ValueError):
+            e.encode_to_host_raw(buf.ctypes.data, buf.size, a.ctypes.data, a.size, b.ctypes.data, b.size - 1)
+        # ids only (offsets_out NULL)
+        a2 = np.empty(ids.size, dtype=np.int32)
+        assert e.encode_to_host_raw(buf.ctypes.data, buf.size, a2.ctypes.data, a2.size, None, 0) == (off.size - 1, ids.size) and np.array_equal(a2, ids)
+        # the resident path still works on the same encoder afterwards
+        assert e.encode_bytes(data)[0].tobytes() == ids.tobytes()
+        e.destroy(); o.destroy()
