@@ -270,7 +270,7 @@ class CudaEncoder {
     // --- the distinct-word table of the call (same sizing and retry rules as the trainer's ingest)
     WordTable wt; std::memset(&wt, 0, sizeof wt);
     uint64_t cap = next_pow2(n / 64 + 1); if (cap < (1u << 16)) cap = 1u << 16;
-    if (cap < wt_cap_hint_) cap = wt_cap_hint_;  // what the previous call of similar size ended with
+    if (cap < wt_cap_hint_ && wt_cap_hint_ <= 64 * cap) cap = wt_cap_hint_;  // what a previous call of similar size ended with
     uint32_t seed = 0x5bd1e995u;
     uint32_t *u_n = reinterpret_cast<uint32_t*>(scal_), *new_list = nullptr, *enc_len = nullptr, *tok_slot = nullptr;
     ull *u_len = nullptr, *enc_off = nullptr, *unit_cnt = nullptr;
