@@ -81,7 +81,6 @@ class CudaEncoder {
 
     // merge dict: filled in file order, so a pair listed twice keeps its LAST id (Python dict assignment, utils/bpe.py:150-153)
     n_merges_ = n;
-    tri_.assign(tri, tri + 3 * n);
     const uint64_t cap = next_pow2(4 * n + 16);
     std::vector<MergeEnt> ent(cap, MergeEnt{0, 0, 0});
     for (size_t m = 0; m < n; m++) {
@@ -443,7 +442,6 @@ class CudaEncoder {
   ull* mirror_dev_ = nullptr;
   ull* scal_ = nullptr;
   size_t n_merges_ = 0;
-  std::vector<int32_t> tri_;
   MergeEnt* d_ent_ = nullptr; MergeTable mt_{};
   ull* d_toff_ = nullptr; uint8_t* d_tbytes_ = nullptr;
   Buf b_text_, b_unit_, b_sums_, b_tok_slot_, b_wt_tag_, b_wt_first_, b_wt_len_, b_wt_bucket_, b_u_slot_, b_u_len_, b_enc_len_, b_enc_off_, b_pool_, b_off_, b_ids_;

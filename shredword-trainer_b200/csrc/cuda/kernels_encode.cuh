@@ -59,8 +59,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) k_enc_words(const uint8_t* __r
         const int32_t r = merge_lookup(mt, x, y);
         if (r < mine) { mine = r; ab = make_int2(x, y); }
       }
-      int32_t best = mine;
-      for (int o = 16; o; o >>= 1) { const int32_t y = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = y < best ? y : best; }
+      const int32_t best = __reduce_min_sync(0xFFFFFFFFu, mine);  // redux.sync: one instruction
       if (best == NO_MERGE) break;
       {  // a merge id belongs to exactly one pair: take it from any lane that found it
         const int src = __ffs(__ballot_sync(0xFFFFFFFFu, mine == best)) - 1;

@@ -60,6 +60,24 @@ def test_fails_loudly_without_gpu(native):
     assert r.returncode != 0 and "created" not in r.stdout and "no CPU fallback" in r.stderr
 
 
+def test_encoder_fails_loudly_without_gpu(native, capfd):
+    """The encoder has no CPU path either: model validation runs on the host, creation needs the device."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "shredword-trainer_b200"))
+    from shredword import BPEEncoder, cbase
+    assert ctypes.sizeof(cbase.EncodeStats) == 8 * 8 + 7 * 8
+    with pytest.raises(ValueError):
+        BPEEncoder(merges=[(97, 98, 257)])          # not what bpe_save writes: rejected before any device call
+    assert "not a BPE model" in capfd.readouterr().err
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ValueError):
+        BPEEncoder(merges=[(97, 98, 256)])
+    assert "CUDA" in capfd.readouterr().err
+    with pytest.raises(RuntimeError):
+        BPEEncoder().encode("no model")
+
+
 def test_generator_is_deterministic(native, tmp_path):
     import hashlib
     a, b = tmp_path / "a.txt", tmp_path / "b.txt"
