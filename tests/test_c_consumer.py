@@ -28,3 +28,15 @@ def test_c_consumer_host_mirrors(native, tmp_path):
 @pytest.mark.gpu
 def test_c_consumer_on_gpu(native, tmp_path):
     _build_and_run(native["lib"], tmp_path)
+
+
+@pytest.mark.gpu
+def test_plain_c_encoder_consumer_on_gpu(native, tmp_path):
+    """tests/c_abi/encoder_consumer.c: the encoder entry points from plain C (gcc -std=c11), end to end on the GPU"""
+    exe = str(tmp_path / "encoder_consumer")
+    libpath = native["lib"]
+    libdir, libname = os.path.dirname(libpath), os.path.basename(libpath)
+    subprocess.run(["gcc", "-O1", "-std=c11", "-Wall", "-o", exe, os.path.join(HERE, "c_abi", "encoder_consumer.c"), "-L" + libdir, "-l:" + libname,
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe, CORPUS, str(tmp_path)], capture_output=True, text=True, env=dict(os.environ, SHRED_QUIET="1"))
+    assert r.returncode == 0 and "0 failed" in r.stdout and "[FAIL]" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
