@@ -366,6 +366,16 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_note = None, None   # DRAM bytes of one launch from the committed ncu capture of this workload (profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic_k_merge_config1_run61.json")))
+        if tr["workload"] == args.workload:
+            traffic = tr["representative"]["traffic_bytes"]
+            traffic_note = {"source": "profiles/r01/ncu_traffic_k_merge_config1_run61.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, merge %d: %s)" % (tr["representative"]["merge"], tr["representative"]["why"]),
+                            "samples": [{"merge": x["merge"], "algorithmic_bytes": x["algorithmic_bytes"], "touched_bytes": x["touched_bytes"],
+                                         "dram_bytes": x["dram_read_bytes"] + x["dram_write_bytes"]} for x in tr["samples"]]}
+    except Exception:
+        pass
     line = {
         "metric": "bpe_train_merges_per_s", "value": total_merges / (train_dev_ms * 1e-3), "unit": "merges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u64",
@@ -375,7 +385,7 @@ def main():
         "gpu_launches": int(sum(s[3]["kernel_launches"] for s in steps)),
         "roofline": {"bound": "hbm", "kernel": "k_merge<4,false> (one cooperative launch per merge: scan | barrier | fold + publish | rewrite)",
                      "achieved": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else 0.0, "peak": peak, "unit": "GB/s",
-                     "frac": all_bytes / (all_ms * 1e-3) / 1e9 / peak if all_ms and peak else None, "traffic": None,
+                     "frac": all_bytes / (all_ms * 1e-3) / 1e9 / peak if all_ms and peak else None, "traffic": traffic, "traffic_detail": traffic_note,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "launches_timed": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
                      "bytes_per_launch": all_bytes / all_n if all_n else None,

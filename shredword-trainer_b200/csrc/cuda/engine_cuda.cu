@@ -26,6 +26,7 @@
 //                       into the pair table + records published | in-place rewrite of the touched words
 //   exchange_deltas ... (multi-GPU) per-merge delta exchange over NVLink peer memory        kernels_dist.cuh
 //   k_token_freq ...... bpe.cpp:409-415                    final token frequencies          kernels_merge.cuh
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -108,6 +109,9 @@ class CudaEngine : public Engine {
     if (const char* pl = std::getenv("SHRED_PLAIN_LAUNCH")) plain_launch_ = *pl && *pl != '0';
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
+    if (const char* pm = std::getenv("SHRED_PROFILE_MERGES")) {  // "0,1,2000": cudaProfilerStart/Stop around these merges (ncu --profile-from-start off)
+      for (const char* q = pm; *q;) { char* end = nullptr; const unsigned long v = std::strtoul(q, &end, 10); if (end == q) break; profile_merges_.push_back(static_cast<uint32_t>(v)); q = *end ? end + 1 : end; }
+    }
     return 0;
   }
 
@@ -584,6 +588,8 @@ class CudaEngine : public Engine {
     const double tl0 = now_ms();
     ++flag_;
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
+    const bool profiled = !profile_merges_.empty() && std::find(profile_merges_.begin(), profile_merges_.end(), merge_no_) != profile_merges_.end();
+    if (profiled) { cudaStreamSynchronize(st_); cudaProfilerStart(); }
     if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
     ull* a_dbg = timed ? dbg_ : nullptr;
@@ -614,6 +620,11 @@ class CudaEngine : public Engine {
     launches_ += 1;
     launch_ms_ += now_ms() - tl0;
     RC(wait_flag());
+    if (profiled) {
+      cudaStreamSynchronize(st_); cudaProfilerStop();
+      std::fprintf(stderr, "[PROFILE]\t merge %u pair (%d,%d): slots %llu (algorithmic %llu bytes), candidate tiles %llu of %u (touched %llu bytes), occurrences %llu\n", merge_no_ - 1, a, b,
+                   static_cast<ull>(n_slots_), 4ull * n_slots_, static_cast<ull>(ctrl_->cand_tiles), n_tiles, (4ull << tile_shift_) * ctrl_->cand_tiles, static_cast<ull>(ctrl_->occ));
+    }
     if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
     if (timed) {
       float ms = 0;
@@ -850,6 +861,7 @@ class CudaEngine : public Engine {
   int timing_every_ = 0;
   ull* dbg_ = nullptr;
   bool dbg_print_ = false, plain_launch_ = false;
+  std::vector<uint32_t> profile_merges_;
   double dbg_acc_[5] = {0, 0, 0, 0, 0};
   uint64_t dbg_n_ = 0;
   int scan_ctas_per_sm_ = 4;
