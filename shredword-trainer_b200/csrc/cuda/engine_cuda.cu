@@ -109,6 +109,7 @@ class CudaEngine : public Engine {
     if (const char* pl = std::getenv("SHRED_PLAIN_LAUNCH")) plain_launch_ = *pl && *pl != '0';
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
+    if (const char* ho = std::getenv("SHRED_HOT_ON_OCC")) hot_on_occ_ = std::strtoull(ho, nullptr, 10);
     if (const char* pm = std::getenv("SHRED_PROFILE_MERGES")) {  // "0,1,2000": cudaProfilerStart/Stop around these merges (ncu --profile-from-start off)
       for (const char* q = pm; *q;) { char* end = nullptr; const unsigned long v = std::strtoul(q, &end, 10); if (end == q) break; profile_merges_.push_back(static_cast<uint32_t>(v)); q = *end ? end + 1 : end; }
     }
@@ -524,6 +525,7 @@ class CudaEngine : public Engine {
     CK(cudaSetDevice(dev_));
     *recs = recs_; *n = 0;
     if (!loaded_) return 0;
+    last_occ_ = ~0ull;  // a fresh pair table: the first merges are the occurrence-heavy ones
     for (int attempt = 0; attempt < 12; ++attempt) {
       CK(cudaMemsetAsync(pt_.ent, 0xFF, pt_.cap * sizeof(PairEnt), st_));
       CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
@@ -610,8 +612,9 @@ class CudaEngine : public Engine {
       DistArgs a_D = dist_;
       if (world_ > 1) a_D = next_exchange();
       bar_count_ += (world_ > 1 ? 2u : 1u) * static_cast<uint32_t>(grid);
+      uint32_t a_hot = last_occ_ >= hot_on_occ_ ? 1u : 0u;  // many occurrences last time: CTAs defer and aggregate their emission (kernels_fold.cuh)
       void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &a_ts, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
-                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &a_dbg, &a_D};
+                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &a_dbg, &a_D, &a_hot};
       const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<4, true>) : reinterpret_cast<const void*>(k_merge<4, false>);
       if (plain_launch_) CK(cudaLaunchKernel(kfn, dim3(grid), dim3(256), args, 0, st_));  // experiment: same grid, no co-residency check by the driver
       else CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
@@ -620,6 +623,7 @@ class CudaEngine : public Engine {
     launches_ += 1;
     launch_ms_ += now_ms() - tl0;
     RC(wait_flag());
+    last_occ_ = ctrl_->occ_local;
     if (profiled) {
       cudaStreamSynchronize(st_); cudaProfilerStop();
       std::fprintf(stderr, "[PROFILE]\t merge %u pair (%d,%d): slots %llu (algorithmic %llu bytes), candidate tiles %llu of %u (touched %llu bytes), occurrences %llu\n", merge_no_ - 1, a, b,
@@ -862,6 +866,8 @@ class CudaEngine : public Engine {
   ull* dbg_ = nullptr;
   bool dbg_print_ = false, plain_launch_ = false;
   std::vector<uint32_t> profile_merges_;
+  uint64_t hot_on_occ_ = 8192;  // SHRED_HOT_ON_OCC: 0 = every launch takes the hot-CTA path (tests), huge = never
+  uint64_t last_occ_ = ~0ull;  // occurrences of the previous merge on this GPU (first merge of a corpus: assume many)
   double dbg_acc_[5] = {0, 0, 0, 0, 0};
   uint64_t dbg_n_ = 0;
   int scan_ctas_per_sm_ = 4;

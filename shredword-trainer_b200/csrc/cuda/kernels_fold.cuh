@@ -115,12 +115,54 @@ __global__ void __launch_bounds__(256) k_finalize_count(DeltaTable dt, PairTable
   finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
 }
 
+// Hot CTAs.  The first merges of a corpus have 10^4-10^6 occurrences: nearly every 128-slot row holds one, so the scan
+// loop would run the long, latency-bound emission (five dependent loads, eight table atomics) once per row with one or two
+// lanes active, on keys that all rows share (merge 0 of the 1 GB corpus: 545 us for a 150 MB scan).  From its HOT_AFTER-th
+// match of a launch on, a CTA therefore only notes the position in shared memory and keeps streaming; after its scan all
+// 256 threads emit the noted occurrences in parallel, aggregating the deltas (sum, minimum sequence number: both
+// associative, so the result is unchanged) in a shared-memory table that is flushed once, before the grid barrier.
+// The host switches this on per launch (hot_on) when the previous merge had many occurrences -- their number falls quickly
+// over the first few hundred merges -- so the sparse launches (nearly all of them) pay nothing for it and keep the immediate
+// path, whose round trips overlap the scan.
+constexpr uint32_t HOT_AFTER = 16, HOT_ML = 3072, HOT_SLOTS = 512, HOT_PROBES = 8;
+struct HotStage {
+  uint32_t seen;              // matches this CTA has met in this launch
+  uint32_t ml[HOT_ML];        // positions noted for the deferred emission (they double as its match-list entries)
+  ull key[HOT_SLOTS];         // ~0 = empty
+  uint32_t lo[HOT_SLOTS], hi[HOT_SLOTS];  // delta sum as two 32-bit halves (shared-memory adds are native for 32 bits only)
+  ull seq[HOT_SLOTS];
+};
+__device__ __forceinline__ void hot_init(HotStage& h) {
+  for (uint32_t i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x) { h.key[i] = ~0ull; h.lo[i] = 0u; h.hi[i] = 0u; h.seq[i] = SEQ_MAX; }
+  if (threadIdx.x == 0) h.seen = 0;
+}
+__device__ __forceinline__ bool hot_add(HotStage& h, uint64_t key, int64_t delta, uint64_t seq) {
+  if (key == ~0ull) return false;  // every pair (x, -1) has this key (sign extension, bpe.cpp:277-278) and it is the table's empty marker
+  uint32_t slot = static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> 55) & (HOT_SLOTS - 1);
+  for (uint32_t probe = 0; probe < HOT_PROBES; ++probe) {
+    ull cur = h.key[slot];
+    if (cur == ~0ull) { const ull prev = atomicCAS(&h.key[slot], ~0ull, static_cast<ull>(key)); cur = prev == ~0ull ? key : prev; }
+    if (cur == key) {
+      const uint32_t d_lo = static_cast<uint32_t>(static_cast<uint64_t>(delta)), d_hi = static_cast<uint32_t>(static_cast<uint64_t>(delta) >> 32);
+      const uint32_t old = atomicAdd(&h.lo[slot], d_lo);
+      const uint32_t up = d_hi + (old + d_lo < old ? 1u : 0u);  // two's complement: exact modulo 2^64
+      if (up) atomicAdd(&h.hi[slot], up);
+      if (seq < *reinterpret_cast<volatile ull*>(&h.seq[slot])) atomicMin(&h.seq[slot], static_cast<ull>(seq));
+      return true;
+    }
+    slot = (slot + 1) & (HOT_SLOTS - 1);
+  }
+  return false;  // crowded: the caller goes to the global table
+}
+
 // One occurrence of (A,B) at flat position p: the four count deltas of bpe.cpp:274-290, computed independently per
 // occurrence.  Left neighbour = the id that stands there when the reference's left-to-right pass reaches p (N if the two
 // symbols before p were themselves merged in this pass), right neighbour = the raw id two slots on.
-__device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
-                                                int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
-                                                uint32_t& my_occ, uint64_t seq_base) {
+// HOT: deferred emission of a hot CTA -- deltas go to its shared-memory table, the match-list entry is already staged.
+template <bool HOT>
+__device__ __forceinline__ void emit_core(const int32_t* ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, int32_t A, int32_t B,
+                                          int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml, uint32_t& my_occ, uint64_t seq_base,
+                                          HotStage& hot) {
   const int32_t l1 = ids[p - 1];
   const uint32_t wi = wid[p];  // independent loads first: wid -> wcnt is the longest chain
   const int32_t r2 = ids[p + 2];
@@ -139,8 +181,41 @@ __device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, 
   const uint64_t key[4] = {fc_key(lid, A), fc_key(lid, N), fc_key(B, rid), fc_key(N, rid)};
   const int64_t delta[4] = {-c, c, -c, c};
   const uint64_t sq[4] = {seq + 0, seq + 1, seq + 2, seq + 3};
-  const uint32_t slot_ml = atomicAdd(&ctr->wl_n, 1u);  // issued before the table updates so its round trip overlaps theirs
-  dt_add4(dt, ctr, key, delta, sq, (l1 >= 0 ? 3u : 0u) | (r2 >= 0 ? 12u : 0u));
-  ml[slot_ml] = static_cast<uint32_t>(p);
+  const uint32_t valid = (l1 >= 0 ? 3u : 0u) | (r2 >= 0 ? 12u : 0u);
   ++my_occ;
+  if (!HOT) {
+    const uint32_t slot_ml = atomicAdd(&ctr->wl_n, 1u);  // issued before the table updates so its round trip overlaps theirs
+    dt_add4(dt, ctr, key, delta, sq, valid);
+    ml[slot_ml] = static_cast<uint32_t>(p);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if ((valid >> j) & 1u) { if (!hot_add(hot, key[j], delta[j], sq[j])) dt_add(dt, ctr, key[j], delta[j], sq[j]); }
+  }
+}
+
+// called from the scan loop for every match: immediate emission, or (hot CTA) just a note
+__device__ __forceinline__ void emit_occurrence(const int32_t* ids, uint64_t p, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt,
+                                                int32_t A, int32_t B, int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml,
+                                                uint32_t& my_occ, uint64_t seq_base, HotStage& hot, bool hot_on) {
+  if (hot_on) {
+    const uint32_t nth = atomicAdd(&hot.seen, 1u);  // shared memory
+    if (nth >= HOT_AFTER && nth - HOT_AFTER < HOT_ML) { hot.ml[nth - HOT_AFTER] = static_cast<uint32_t>(p); return; }
+  }
+  emit_core<false>(ids, p, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, seq_base, hot);
+}
+
+// all threads of the CTA, after a __syncthreads() that follows its scan: emit what was noted, flush table and match list
+__device__ __forceinline__ void hot_finish(HotStage& h, const int32_t* ids, const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, int32_t A, int32_t B,
+                                           int32_t N, const Params& P, const DeltaTable& dt, DevCounters* ctr, uint32_t* ml, uint32_t& my_occ, uint64_t seq_base,
+                                           uint32_t* s_base) {
+  if (h.seen <= HOT_AFTER) return;  // uniform
+  const uint32_t staged = min(h.seen - HOT_AFTER, HOT_ML);
+  if (threadIdx.x == 0) *s_base = atomicAdd(&ctr->wl_n, staged);
+  for (uint32_t i = threadIdx.x; i < staged; i += blockDim.x) emit_core<true>(ids, h.ml[i], wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, seq_base, h);
+  __syncthreads();
+  const uint32_t base = *s_base;
+  for (uint32_t i = threadIdx.x; i < staged; i += blockDim.x) ml[base + i] = h.ml[i];  // (A,A) runs: second halves ride along; phase 3 only needs the words
+  for (uint32_t i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x)
+    if (h.key[i] != ~0ull) dt_add(dt, ctr, h.key[i], static_cast<int64_t>((static_cast<uint64_t>(h.hi[i]) << 32) | h.lo[i]), h.seq[i]);
 }

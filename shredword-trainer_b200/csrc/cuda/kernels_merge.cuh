@@ -16,10 +16,13 @@ __global__ void __launch_bounds__(256, 4) k_merge(int4* ids4, uint32_t n4, uint3
                                                const uint32_t* __restrict__ wid, const ull* __restrict__ wcnt, const ull* __restrict__ woff, uint32_t* wlen,
                                                uint32_t* claimed, uint32_t merge_no, int32_t A, int32_t B, int32_t N, Params P, DeltaTable dt, PairTable pt,
                                                DevCounters* ctr, uint32_t* __restrict__ ml, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, uint64_t flag_value,
-                                               uint32_t bar_base, ull* dbg, DistArgs D) {
+                                               uint32_t bar_base, ull* dbg, DistArgs D, uint32_t hot_on) {
   __shared__ uint32_t cand[MAX_TILES_PER_CTA];
   __shared__ uint32_t n_cand;
   __shared__ bool last;
+  __shared__ HotStage hot;
+  __shared__ uint32_t hot_base;
+  if (hot_on) hot_init(hot);  // ordered before the first emit_occurrence by the __syncthreads() of the candidate search below
   int32_t* ids = reinterpret_cast<int32_t*>(ids4);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[0] = gtime();
@@ -71,11 +74,15 @@ __global__ void __launch_bounds__(256, 4) k_merge(int4* ids4, uint32_t n4, uint3
         while (m) {
           const int k = __ffs(m) - 1;
           m &= m - 1;
-          emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull);
+          emit_occurrence(ids, p0 + k, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull, hot, hot_on != 0);
         }
       }
     }
   }
+  }
+  if (hot_on) {  // uniform
+    __syncthreads();
+    hot_finish(hot, ids, wid, wcnt, A, B, N, P, dt, ctr, ml, my_occ, DIST ? (static_cast<uint64_t>(D.rank) << kSeqRankShift) : 0ull, &hot_base);
   }
   for (int o = 16; o; o >>= 1) my_occ += __shfl_down_sync(0xFFFFFFFFu, my_occ, o);
   if (lane == 0 && my_occ) atomicAdd(&ctr->occ, static_cast<ull>(my_occ));
