@@ -254,7 +254,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["SHRED_QUIET"] = "1"
-    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "16")  # CUDA events around every 16th merge kernel
+    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "64")  # CUDA events around every 64th merge kernel (a timed merge cannot overlap its rewrite phase with the host)
     os.environ["SHRED_DEVICE"] = str(local_rank)
     sharded = world > 1 and not args.replicas
     if sharded:
@@ -389,7 +389,7 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "launches_timed": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
                      "bytes_per_launch": all_bytes / all_n if all_n else None,
-                     "note": "achieved = ALGORITHMIC bytes (4 B x symbol slots, SURVEY 8d B_merge) / CUDA-event duration of the whole kernel, averaged over every 16th "
+                     "note": "achieved = ALGORITHMIC bytes (4 B x symbol slots, SURVEY 8d B_merge) / CUDA-event duration of the whole kernel, averaged over every 64th "
                              "launch of the timed region. The kernel reads fewer bytes than that: a tile occurrence index skips tiles that cannot hold the pair "
                              "(touched_gbs = bytes actually scanned / duration), and its duration is mostly a latency chain (delta emission, grid barrier, "
                              "pair-table fold, host flag, rewrite), see DESIGN.md section 5. ncu --set full (profiles/): a dense launch reads 31.7 MB of DRAM for "

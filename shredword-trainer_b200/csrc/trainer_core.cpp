@@ -202,16 +202,18 @@ void TrainerCore::apply_records(const Rec* recs, size_t n) {
   // then order each bucket's handful of records by descending sequence.
   if (bucket_head_.empty()) bucket_head_.assign(1024, -1);
   next_in_bucket_.resize(n);
+  uint64_t used[16] = {0};  // non-empty buckets: a merge touches ~55 of the 1024, so walk set bits instead of all heads
   for (size_t i = 0; i < n; i++) {
     if (recs[i].serial == REC_NO_SERIAL) version_.prefetch(recs[i].key); else if (recs[i].serial < ver_.size()) __builtin_prefetch(&ver_[recs[i].serial]);
     const uint32_t b = static_cast<uint32_t>(recs[i].key & 1023u);
     next_in_bucket_[i] = bucket_head_[b];
     bucket_head_[b] = static_cast<int32_t>(i);
+    used[b >> 6] |= 1ull << (b & 63u);
   }
   order_idx_.clear();
-  for (uint32_t b = 0; b < 1024; b++) {
+  for (uint32_t w = 0; w < 16; w++) for (uint64_t bits = used[w]; bits; bits &= bits - 1) {
+    const uint32_t b = (w << 6) + static_cast<uint32_t>(__builtin_ctzll(bits));
     int32_t i = bucket_head_[b];
-    if (i < 0) continue;
     bucket_head_[b] = -1;
     const size_t start = order_idx_.size();
     for (; i >= 0; i = next_in_bucket_[i]) {  // insertion sort, descending sequence
