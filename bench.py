@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- BPE train() throughput on B200 (BASELINE.json: "BPE train() wall-s & merges/s, 32k vocab ...").
 
-A "step" is one full pass of the hot path over the synthetic corpus: bpe_load_corpus (host buffer -> HBM -> unique-word
-table) + bpe_train (pair count + merge loop) + reading the merge list back.
+A "step" is one full pass of the hot path over the synthetic corpus, through the reference's own call sequence
+(shredword/trainer.py:12-29): bpe_load_corpus(path) -> bpe_train -> bpe_save(model, vocab).
+Default workload: BASELINE.json's headline configuration (32k vocab / 10 GB, configs[2]) at every N.
   value  merges/s of bpe_train() alone, corpus already resident in HBM, timed with CUDA events on the library's stream
-  e2e    merges/s through the C ABI with HOST buffers: pinned corpus bytes -> load -> train -> merge list on the host
+  e2e    merges/s through the drop-in C ABI with HOST data: corpus file in host memory (tmpfs / page cache) ->
+         bpe_load_corpus(path) (pinned staging ring, H2D inside) -> bpe_train -> bpe_save (both files written)
   roofline      the dominant kernel (k_merge, one cooperative launch per merge): algorithmic bytes / CUDA-event duration
   cpu_baseline  the unmodified reference (oracle/_ref, pinned with the zero-fill malloc shim) on a bounded sample
 
@@ -34,6 +36,11 @@ WORKLOADS = {
     "config4_50GB": (50_000_000_000, 1, 25, "zipf", 131072, 0, 0.995, 2000),
     "tiny": (4_000_000, 1, 16, "zipf", 2000, 0, 0.995, 20),
 }
+ROOFLINE_NOTE = ("achieved = ALGORITHMIC bytes of the scan formulation (SURVEY 8d B_merge = 4 B x (live symbols + unique words) per merge) / CUDA-event "
+                 "duration of the whole per-merge kernel, averaged over every 64th launch of the timed region. It is an EFFECTIVE rate: the kernel reads far fewer "
+                 "bytes than that (touched_gbs = bytes it actually reads / duration) and its duration is a chain of dependent memory round trips, not a stream; "
+                 "see DESIGN.md sections 4-5 and roofline.traffic for measured DRAM bytes.")
+DENSE_NOTE = "timed launches of the occurrence-heavy early merges"
 REF_SAMPLE_BYTES = 16 << 20   # bounded sample for the CPU reference: first 16 MiB of the corpus ...
 REF_SAMPLE_MERGES = 40        # ... and this many merges (the reference needs ~47 min just to load 1 GB)
 
@@ -93,7 +100,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_sample(corpus_path, cfg, steps=1, warmup=0):
+def reference_sample(corpus_path, cfg, steps=1, warmup=0, workload=None):
     """The unmodified reference (oracle/_ref) on a bounded sample of the workload; falls back to the C oracle port."""
     from oracle_lib import REF_HARNESS, REF_SO, ZMALLOC, have_reference
     vocab, unk, cov, mf = cfg
@@ -129,7 +136,17 @@ def reference_sample(corpus_path, cfg, steps=1, warmup=0):
     load_s = sum(r[0] for r in runs) / len(runs)
     train_s = sum(r[1] for r in runs) / len(runs)
     merges = runs[0][2]
-    return {"value": merges / train_s if train_s > 0 else 0.0, "unit": "merges/s", "cores": 1, "kind": kind,
+    full = None
+    try:  # the one full-size run of the unmodified reference on this workload (dev container), recorded beside its golden vector
+        full = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"][workload].get("reference_full_run")
+        if full:
+            full = dict(full, merges_per_s=full["merges"] / full["train_s"], note="recorded once, not timed in this run")
+    except Exception:
+        pass
+    return {"value": merges / train_s if train_s > 0 else 0.0, "unit": "merges/s", "cores": 1, "kind": kind, "same_work": False,
+            "same_work_note": "the reference needs hours to load and train the full workload (its merges/s FALLS with corpus size: per-merge cost is two scans of all "
+                              "symbols), so it is timed on a bounded sample; value / this number is therefore a LOWER BOUND on the like-for-like speed-up",
+            "full_workload_recorded": full,
             "sample": f"first {nbytes} bytes of the corpus, bpe_init + {merges} merges (train part only; load of the sample took {load_s:.2f} s); "
                       f"the reference is single-threaded",
             "load_s": load_s, "train_s": train_s, "merges": merges, "sample_bytes": nbytes}
@@ -218,8 +235,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("SHRED_BENCH_WORKLOAD", "config1_1GB"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("SHRED_BENCH_WORKLOAD", "config2_10GB"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the informational load_buffer and encoder legs (they pin a corpus-sized host buffer)")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas per GPU instead of one sharded job")
     args = ap.parse_args()
 
@@ -238,15 +256,15 @@ def main():
         if rank != 0:
             return
         corpus = make_corpus(args.workload)
-        cb = reference_sample(corpus, (vocab, unk, cov, mf), steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+        cb = reference_sample(corpus, (vocab, unk, cov, mf), steps=max(min(args.steps, 3), 1), warmup=min(args.warmup, 1), workload=args.workload)
         line = {"impl": "reference", "metric": "bpe_train_merges_per_s", "value": cb["value"], "unit": "merges/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * (cb["train_s"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "dtype": "u64", "data": "synthetic", "config": config, "cpu_baseline": cb, "same_work": False,
                 "e2e": {"value": cb["value"], "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
 
-    import numpy as np
+    import hashlib
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -254,7 +272,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["SHRED_QUIET"] = "1"
-    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "64")  # CUDA events around every 64th merge kernel (a timed merge cannot overlap its rewrite phase with the host)
+    os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "64")  # CUDA events around every 64th merge kernel
     os.environ["SHRED_DEVICE"] = str(local_rank)
     sharded = world > 1 and not args.replicas
     if sharded:
@@ -273,11 +291,10 @@ def main():
     if world > 1:
         dist.barrier()
         corpus = make_corpus(args.workload, rank)
-    # host buffer: pinned memory holding the corpus bytes (the "HOST buffers" of the end-to-end leg)
     size = os.path.getsize(corpus)
-    host = torch.empty(size, dtype=torch.uint8, pin_memory=True)
-    with open(corpus, "rb") as f:
-        f.readinto(host.numpy())
+    out_dir = os.path.join(scratch_dir(), f"out_rank{rank}")
+    os.makedirs(out_dir, exist_ok=True)
+    model_path, vocab_path = os.path.join(out_dir, "bpe.model"), os.path.join(out_dir, "bpe.vocab")
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,24 +302,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step():
+    def one_step(buffer=None):
+        """The reference's call sequence (shredword/trainer.py:12-29) on the drop-in ABI; buffer != None: the load_buffer extension."""
         t = BPETrainer(vocab, unk, cov, mf)
         t0 = time.perf_counter()
-        t.load_bytes(host)
+        if buffer is None:
+            t.load_corpus(corpus)          # bpe_load_corpus(path): host file -> pinned staging ring -> HBM -> unique-word table
+        else:
+            t.load_bytes(buffer)
         t1 = time.perf_counter()
-        n = t.train()
-        merges = t.merges()  # merge list read on the host (Trainer.merge_ops mirror)
+        n = t.train()                      # bpe_train
         t2 = time.perf_counter()
+        t.save(model_path, vocab_path)     # bpe_save: token frequencies from the device, both files written
+        t3 = time.perf_counter()
         st = t.stats()
         t.destroy()
-        return n, t1 - t0, t2 - t1, st, merges
+        out_bytes = os.path.getsize(model_path) + os.path.getsize(vocab_path)
+        return {"merges": n, "load_s": t1 - t0, "train_s": t2 - t1, "save_s": t3 - t2, "st": st, "out_bytes": out_bytes}
 
     import contextlib
     import io
     quiet = contextlib.redirect_stdout(io.StringIO())
+    cold = None
     with quiet:
-        for _ in range(args.warmup):
-            one_step()
+        for i in range(args.warmup):
+            r = one_step()
+            if i == 0:
+                cold = r  # the first load/train of this process: allocator pool, pinned staging ring and module load included
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -314,14 +340,21 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.finish()
+    model_bytes = open(model_path, "rb").read()   # the file bpe_save wrote in the last timed step
+    merges_md5 = hashlib.md5(model_bytes).hexdigest()
+    vocab_md5 = hashlib.md5(open(vocab_path, "rb").read()).hexdigest()
+    merges_list = [tuple(int.from_bytes(model_bytes[12 * i + 4 * j:12 * i + 4 * j + 4], "little", signed=True) for j in range(3)) for i in range(len(model_bytes) // 12)] if world == 1 else None
 
-    # informational: the same load through bpe_load_corpus(path) (file in the page cache -> mmap -> HBM), outside the timed region
-    load_file_s = None
-    if world == 1:
+    # informational: the same step through the bpe_b200_load_buffer extension (pinned host buffer), outside the timed region
+    host, side_buffer = None, None
+    if world == 1 and not args.no_side_legs:
+        host = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        with open(corpus, "rb") as f:
+            f.readinto(host.numpy())
         with quiet:
-            tf = BPETrainer(vocab, unk, cov, mf)
-            t0 = time.perf_counter(); tf.load_corpus(corpus); load_file_s = time.perf_counter() - t0
-            tf.destroy()
+            rb = one_step(buffer=host)
+        side_buffer = {"what": "same step with bpe_b200_load_buffer (one cudaMemcpyAsync from a pinned host buffer) instead of bpe_load_corpus(path); 1 run",
+                       "value": rb["merges"] / (rb["load_s"] + rb["train_s"] + rb["save_s"]), "unit": "merges/s", "load_s": rb["load_s"]}
     # informational (N>1, sharded default): the same GPUs as N independent replicas -- one full trainer per GPU, no exchange
     replicas = None
     if sharded:
@@ -331,83 +364,84 @@ def main():
             rstep = one_step()
         barrier()
         os.environ.update(saved)
-        rt = torch.tensor([rstep[3]["train_device_ms"], rstep[1] + rstep[2]], dtype=torch.float64, device="cuda")
+        rt = torch.tensor([rstep["st"]["train_device_ms"], rstep["load_s"] + rstep["train_s"] + rstep["save_s"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(rt, op=dist.ReduceOp.MAX)
         replicas = {"what": f"{world} independent trainers (one per GPU) on the same workload, 1 step, max over ranks",
-                    "value": world * rstep[0] / (rt[0].item() * 1e-3), "e2e": world * rstep[0] / rt[1].item(), "unit": "merges/s", "scaling": "weak"}
+                    "value": world * rstep["merges"] / (rt[0].item() * 1e-3), "e2e": world * rstep["merges"] / rt[1].item(), "unit": "merges/s", "scaling": "weak"}
     encoder = None
-    if world == 1:
+    if world == 1 and host is not None:
         try:
-            encoder = encoder_leg(host, size, steps[-1][4], peak_hint=None, with_cpu=not args.no_cpu_baseline)
+            encoder = encoder_leg(host, size, merges_list, peak_hint=None, with_cpu=not args.no_cpu_baseline)
         except Exception as e:  # informational leg: never takes the headline measurement down
             encoder = {"error": str(e)}
-    merges = steps[0][0]
-    train_dev_ms = sum(s[3]["train_device_ms"] for s in steps)
-    e2e_s = sum(s[1] + s[2] for s in steps)
+    merges = steps[0]["merges"]
+    train_dev_ms = sum(s["st"]["train_device_ms"] for s in steps)
+    e2e_s = sum(s["load_s"] + s["train_s"] + s["save_s"] for s in steps)
+    phase = [sum(s[k] for s in steps) / args.steps for k in ("load_s", "train_s", "save_s")]
     # max over ranks
     if world > 1:
-        tt = torch.tensor([train_dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([train_dev_ms, e2e_s, wall] + phase, dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        train_dev_ms, e2e_s, wall = tt.tolist()
+        train_dev_ms, e2e_s, wall = tt.tolist()[:3]
+        phase = tt.tolist()[3:]
     total_merges = merges * args.steps * (1 if sharded or world == 1 else world)
-    st = steps[-1][3]
-    all_ms = sum(s[3]["scan_device_ms"] for s in steps)
-    all_bytes = sum(s[3]["scan_bytes"] for s in steps)
-    all_touched = sum(s[3]["scan_bytes_touched"] for s in steps)
-    all_n = sum(s[3]["scan_launches"] for s in steps)
-    scan_ms = sum(s[3]["dense_device_ms"] for s in steps)
-    scan_bytes = sum(s[3]["dense_bytes"] for s in steps)
-    scan_n = sum(s[3]["dense_launches"] for s in steps)
-    dense_phase_ms = sum(s[3]["dense_phase_ms"] for s in steps)
-    all_phase_ms = sum(s[3]["scan_phase_ms"] for s in steps)
+    st = steps[-1]["st"]
+    S = lambda k: sum(s["st"][k] for s in steps)  # noqa: E731
+    all_ms, all_bytes, all_touched, all_n = S("scan_device_ms"), S("scan_bytes"), S("scan_bytes_touched"), S("scan_launches")
+    dense_ms, dense_bytes, dense_n, dense_phase_ms, all_phase_ms = S("dense_device_ms"), S("dense_bytes"), S("dense_launches"), S("dense_phase_ms"), S("scan_phase_ms")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic, traffic_note = None, None   # DRAM bytes of one launch from the committed ncu capture of this workload (profiles/)
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic_k_merge_config1_run61.json")))
-        if tr["workload"] == args.workload:
-            traffic = tr["representative"]["traffic_bytes"]
-            traffic_note = {"source": "profiles/r01/ncu_traffic_k_merge_config1_run61.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, merge %d: %s)" % (tr["representative"]["merge"], tr["representative"]["why"]),
-                            "samples": [{"merge": x["merge"], "algorithmic_bytes": x["algorithmic_bytes"], "touched_bytes": x["touched_bytes"],
-                                         "dram_bytes": x["dram_read_bytes"] + x["dram_write_bytes"]} for x in tr["samples"]]}
-    except Exception:
-        pass
+    traffic, traffic_note = None, None   # DRAM bytes per launch from a committed ncu capture OF THIS WORKLOAD (profiles/), else null
+    for cand in sorted(__import__("glob").glob(os.path.join(ROOT, "profiles", "r0*", "ncu_traffic_*.json")), reverse=True):
+        try:
+            tr = json.load(open(cand))
+            if tr.get("workload") == args.workload:
+                traffic = tr["representative"]["traffic_bytes"]
+                traffic_note = {"source": os.path.relpath(cand, ROOT) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch: %s)" % tr["representative"].get("why", ""),
+                                "samples": tr.get("samples")}
+                break
+        except Exception:
+            pass
     line = {
         "metric": "bpe_train_merges_per_s", "value": total_merges / (train_dev_ms * 1e-3), "unit": "merges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": config, "clocks": clocks,
-        "e2e": {"value": total_merges / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]) + 8 * merges,
-                "load_s_per_step": sum(s[1] for s in steps) / args.steps, "train_s_per_step": sum(s[2] for s in steps) / args.steps},
-        "gpu_launches": int(sum(s[3]["kernel_launches"] for s in steps)),
-        "roofline": {"bound": "hbm", "kernel": "k_merge<4,false> (one cooperative launch per merge: scan | barrier | fold + publish | rewrite)",
+        "e2e": {"value": total_merges / e2e_s, "unit": "merges/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]) + int(steps[-1]["out_bytes"]),
+                "what": "bpe_load_corpus(path) + bpe_train + bpe_save through the drop-in C ABI (the reference's call sequence, shredword/trainer.py:12-29); corpus file in host "
+                        "memory (tmpfs), both output files written; max over ranks",
+                "load_s_per_step": phase[0], "train_s_per_step": phase[1], "save_s_per_step": phase[2],
+                "cold_first_step": {"load_s": cold["load_s"], "train_s": cold["train_s"], "save_s": cold["save_s"],
+                                    "what": "first step of the process (warm-up 0): allocator pool growth, pinned staging ring, lazy module load included"} if cold else None,
+                "load_buffer_variant": side_buffer},
+        "gpu_launches": int(S("kernel_launches")),
+        "roofline": {"bound": "hbm", "kernel": st.get("merge_kernel_name", "k_merge (one launch per merge)") if isinstance(st, dict) else "k_merge",
                      "achieved": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else 0.0, "peak": peak, "unit": "GB/s",
                      "frac": all_bytes / (all_ms * 1e-3) / 1e9 / peak if all_ms and peak else None, "traffic": traffic, "traffic_detail": traffic_note,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "launches_timed": int(all_n), "avg_launch_us": 1e3 * all_ms / all_n if all_n else None,
                      "bytes_per_launch": all_bytes / all_n if all_n else None,
-                     "note": "achieved = ALGORITHMIC bytes (4 B x symbol slots, SURVEY 8d B_merge) / CUDA-event duration of the whole kernel, averaged over every 64th "
-                             "launch of the timed region. The kernel reads fewer bytes than that: a tile occurrence index skips tiles that cannot hold the pair "
-                             "(touched_gbs = bytes actually scanned / duration), and its duration is mostly a latency chain (delta emission, grid barrier, "
-                             "pair-table fold, host flag, rewrite), see DESIGN.md section 5. ncu --set full (profiles/): a dense launch reads 31.7 MB of DRAM for "
-                             "31.3 MB of algorithmic bytes (no re-reads); the stand-alone scan kernel of run 1 streamed at 4.76 TB/s = 73 % of the measured peak.",
+                     "note": ROOFLINE_NOTE,
                      "touched_gbs": all_touched / (all_ms * 1e-3) / 1e9 if all_ms else None,
-                     "tiles_scanned_frac": st["cand_tiles"] / st["tiles_total"] if st["tiles_total"] else None,
-                     "dense_launches": {"what": "timed launches that scanned >= 90 % of the tiles (early, occurrence-heavy merges)", "n": int(scan_n),
-                                        "avg_launch_us": 1e3 * scan_ms / scan_n if scan_n else None,
-                                        "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms else None,
-                                        "scan_phase_gbs": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 if dense_phase_ms else None,
-                                        "scan_phase_frac": scan_bytes / (dense_phase_ms * 1e-3) / 1e9 / peak if dense_phase_ms and peak else None},
+                     "dense_launches": {"what": DENSE_NOTE, "n": int(dense_n),
+                                        "avg_launch_us": 1e3 * dense_ms / dense_n if dense_n else None,
+                                        "achieved": dense_bytes / (dense_ms * 1e-3) / 1e9 if dense_ms else None,
+                                        "scan_phase_gbs": dense_bytes / (dense_phase_ms * 1e-3) / 1e9 if dense_phase_ms else None,
+                                        "scan_phase_frac": dense_bytes / (dense_phase_ms * 1e-3) / 1e9 / peak if dense_phase_ms and peak else None},
                      "scan_phase_avg_us_all_launches": 1e3 * all_phase_ms / all_n if all_n else None},
         "detail": {"merges_per_step": merges, "n_words": int(st["n_words"]), "n_symbols_initial": int(st["n_symbols_initial"]), "n_symbols_final": int(st["n_symbols_live"]),
                    "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
+                   "tie_rate_upper": st["tie_root_equal"] / merges if merges else None, "tie_rate_lower": st["tie_same_as_prev"] / merges if merges else None,
+                   "tie_note": "SURVEY A15: share of merges whose frequency equals that of the entry left at the heap root (upper bound on a tied maximum) / the previous merge's frequency (lower bound)",
                    "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
                    "ingest_device_ms": st["ingest_device_ms"], "ingest_gbs": st["ingest_bytes"] / (st["ingest_device_ms"] * 1e-3) / 1e9 if st["ingest_device_ms"] else None,
                    "count_device_ms": st["count_device_ms"], "count_gbs": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 if st["count_device_ms"] else None,
-                   "h2d_ms": st["h2d_ms"], "load_corpus_from_file_s": load_file_s, "load_s_steps": [round(x[1], 4) for x in steps], "train_s_steps": [round(x[2], 4) for x in steps], "merges_md5": __import__("hashlib").md5(b"".join(__import__("struct").pack("<3i", *m) for m in steps[-1][4])).hexdigest(),
+                   "count_frac_of_hbm_peak": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 / peak if st["count_device_ms"] and peak else None,
+                   "h2d_ms": st["h2d_ms"], "load_s_steps": [round(x["load_s"], 4) for x in steps], "train_s_steps": [round(x["train_s"], 4) for x in steps],
+                   "save_s_steps": [round(x["save_s"], 4) for x in steps], "merges_md5": merges_md5, "vocab_md5": vocab_md5,
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
     }
     if replicas:
@@ -420,7 +454,9 @@ def main():
         big = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"].get(args.workload)
         if big:
             line["detail"]["golden_merges_md5"] = big["merges_md5"]
-            line["detail"]["bit_exact_vs_golden"] = big["merges_md5"] == line["detail"]["merges_md5"] and big["merges"] == merges
+            line["detail"]["bit_exact_vs_golden"] = big["merges_md5"] == merges_md5 and big["merges"] == merges
+            if big.get("vocab_md5"):
+                line["detail"]["vocab_bit_exact_vs_golden"] = big["vocab_md5"] == vocab_md5
     except Exception:
         pass
     if sharded and rank == 0:
@@ -429,15 +465,9 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = reference_sample(corpus, (vocab, unk, cov, mf))
+                line["cpu_baseline"] = reference_sample(corpus, (vocab, unk, cov, mf), workload=args.workload)
             except Exception as e:  # the checker must never take the measurement down
                 line["cpu_baseline"] = {"value": None, "unit": "merges/s", "cores": 1, "kind": "unavailable", "sample": str(e)}
-            try:  # the one full-size run of the unmodified reference on this workload, recorded beside its golden vector
-                full = json.load(open(os.path.join(ROOT, "tests", "golden", "big.json")))["cases"][args.workload].get("reference_full_run")
-                if full:
-                    line["cpu_baseline"]["full_workload_recorded"] = dict(full, merges_per_s=full["merges"] / full["train_s"], note="not timed in this run")
-            except Exception:
-                pass
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -116,6 +116,9 @@ typedef struct shred_stats_t {
   uint64_t cand_tiles, tiles_total; /* candidate / total tiles summed over all merges of the last train */
   double scan_phase_ms, dense_phase_ms; /* in-kernel timer: start -> end of the scan phase, all / dense timed launches */
   uint64_t h2d_bytes, d2h_bytes;
+  /* tie statistics of the last train: merges whose frequency equals that of the entry left at the heap
+   * root (upper bound on "another pair shares the maximum") / equals the previous merge's frequency (lower bound) */
+  uint64_t tie_root_equal, tie_same_as_prev;
 } shred_stats_t;
 SHRED_API int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);
 /* Debug/parity getters: copy the current word table out of HBM.  word order = reference StrMap iteration order.

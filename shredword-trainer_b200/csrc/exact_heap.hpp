@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -32,7 +33,15 @@ static_assert(sizeof(HeapPayload) == 16, "payload packs into 16 bytes");
 class ExactHeap {
  public:
   ~ExactHeap() { release(freq_, cap_ * sizeof(uint64_t)); release(pay_, cap_ * sizeof(HeapPayload)); }
-  void clear() { n_ = 0; dirty_ = true; }
+  void clear() { n_ = 0; dirty_ = true; touched_.clear(); }
+  // Step-wise C consumers read Trainer.heap.data after every bpe_merge_batch call: while tracking is on, push/pop note the
+  // slots they write so that materialize() patches those few entries instead of rebuilding the whole mirror (O(heap)).
+  void set_tracking(bool on) {
+    if (on == track_) return;
+    track_ = on;
+    touched_.clear();
+    dirty_ = true;  // the slots written while the mode changed are unknown: next materialize() rebuilds once
+  }
   size_t size() const { return n_; }
   bool empty() const { return n_ == 0; }
   HeapEnt top() const { return HeapEnt{pay_[1].key, freq_[1], pay_[1].version, pay_[1].serial}; }
@@ -46,11 +55,12 @@ class ExactHeap {
       if (freq_[p] >= freq) break;
       freq_[s] = freq_[p];
       pay_[s] = pay_[p];
+      if (track_) note(s);
       s = p;
     }
     freq_[s] = freq;
     pay_[s] = HeapPayload{key, version, serial};
-    dirty_ = true;
+    if (track_) note(s); else dirty_ = true;
     ++pushes;
   }
 
@@ -83,22 +93,27 @@ class ExactHeap {
     for (int k = 0; k < depth; k++) {
       freq_[at] = freq_[path[k]];
       pay_[at] = pay_[path[k]];
+      if (track_) note(at);
       at = path[k];
     }
-    if (n_) { freq_[at] = xf; pay_[at] = xp; }
-    dirty_ = true;
+    if (n_) { freq_[at] = xf; pay_[at] = xp; if (track_) note(at); }
+    if (!track_) dirty_ = true;
     ++pops;
     return out;
   }
 
   // The reference's array of 24-byte entries, rebuilt only when the heap changed since the last call.
   BPEHeapEntry* materialize(size_t* cap_out) {
-    if (dirty_) {
+    if (dirty_ || !mirror_valid_) {
       mirror_.resize(n_ ? n_ : 1);
       HeapEnt* m = reinterpret_cast<HeapEnt*>(mirror_.data());
       for (size_t i = 0; i < n_; i++) m[i] = HeapEnt{pay_[i + 1].key, freq_[i + 1], pay_[i + 1].version, pay_[i + 1].serial};
-      dirty_ = false;
+    } else if (!touched_.empty()) {  // patch only the slots written since the last call
+      if (mirror_.size() < (n_ ? n_ : 1)) mirror_.resize(std::max(n_ ? n_ : 1, mirror_.size() * 2));
+      HeapEnt* m = reinterpret_cast<HeapEnt*>(mirror_.data());
+      for (const size_t s : touched_) if (s <= n_) m[s - 1] = HeapEnt{pay_[s].key, freq_[s], pay_[s].version, pay_[s].serial};
     }
+    dirty_ = false; mirror_valid_ = true; touched_.clear();
     if (cap_out) *cap_out = mirror_.capacity();
     return mirror_.data();
   }
@@ -126,11 +141,17 @@ class ExactHeap {
     freq_ = nf; pay_ = np; cap_ = nc;
   }
 
+  void note(size_t s) {
+    if (dirty_) return;
+    if (touched_.size() * 8 > n_ + 1024) { dirty_ = true; touched_.clear(); return; }  // cheaper to rebuild everything
+    touched_.push_back(s);
+  }
   uint64_t* freq_ = nullptr;
   HeapPayload* pay_ = nullptr;
   size_t n_ = 0, cap_ = 0;
   std::vector<BPEHeapEntry> mirror_;
-  bool dirty_ = true;
+  std::vector<size_t> touched_;
+  bool dirty_ = true, mirror_valid_ = false, track_ = false;
 };
 
 static_assert(sizeof(HeapEnt) == sizeof(BPEHeapEntry) && sizeof(HeapEnt) == 24, "heap entry layout (reference heap.h:17-21)");

@@ -248,7 +248,12 @@ void TrainerCore::apply_records(const Rec* recs, size_t n) {
   }
 }
 
-int TrainerCore::merge_batch(int batch_size) {
+int TrainerCore::merge_batch(int batch_size) {  // the ABI's step-wise entry: C consumers read Trainer.heap after every call
+  heap_.set_tracking(true);
+  return merge_loop(batch_size);
+}
+
+int TrainerCore::merge_loop(int batch_size) {
   if (heap_.empty()) {  // bpe.cpp:237-240
     if (!quiet_) std::printf("[INFO]\t Heap is empty, no more merges possible\n");
     return 0;
@@ -273,6 +278,12 @@ int TrainerCore::merge_batch(int batch_size) {
       continue;
     }
     host_heap_ms_ += now_ms() - h_open;
+    // tie statistics: a device argmax could only pick this merge if no other mergeable pair shares its
+    // frequency.  Upper bound: the entry now at the root has the same frequency (it may be stale); lower bound: the previous
+    // merge had the same frequency.
+    if (!heap_.empty() && heap_.top().freq == top.freq) ++tie_root_equal_;
+    if (top.freq == last_merge_freq_) ++tie_same_as_prev_;
+    last_merge_freq_ = top.freq;
     // a current entry of a pair without unk_id carries the exact table frequency, which is >= min_pair_freq
     const int32_t new_id = static_cast<int32_t>(256 + abi_->num_merges);  // bpe.cpp:259
     if (abi_->num_merges < merge_cap_) abi_->merge_ops[abi_->num_merges] = top.key;  // bpe.cpp:261
@@ -301,6 +312,8 @@ int TrainerCore::train() {  // bpe.cpp:345-386
   eng_->mark_begin();
   host_heap_ms_ = 0; occurrences_ = 0;
   heap_.pushes = heap_.pops = 0;
+  tie_root_equal_ = tie_same_as_prev_ = 0; last_merge_freq_ = ~0ull;
+  heap_.set_tracking(false);  // one rebuild of the Trainer.heap mirror at the end instead of noting every written slot
   if (!quiet_) std::printf("[INFO]\t Starting BPE training (target vocab size: %zu)\n", abi_->config.target_vocab_size);
   init();
   int total = 0;
@@ -310,7 +323,7 @@ int TrainerCore::train() {  // bpe.cpp:345-386
     if (heap_.empty()) { if (!quiet_) std::printf("[INFO]\t Heap exhausted, stopping training\n"); break; }
     // the reference sizes its batches from the top frequency (bpe.cpp:362-368); batch boundaries have no effect on the
     // result, so one call covers the remaining merges
-    int merged = merge_batch(target - total);
+    int merged = merge_loop(target - total);
     if (merged <= 0) { if (!quiet_) std::printf("[WARNING]\t No merges performed, stopping\n"); break; }
     total += merged;
   }
@@ -383,6 +396,7 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->load_wall_ms = load_wall_ms_; s->h2d_ms = es.h2d_ms; s->train_wall_ms = train_wall_ms_; s->train_device_ms = train_device_ms_; s->host_heap_ms = host_heap_ms_;
   s->wait_ms = es.wait_ms; s->launch_ms = es.launch_ms; s->save_wall_ms = save_wall_ms_;
   s->h2d_bytes = es.h2d_bytes; s->d2h_bytes = es.d2h_bytes;
+  s->tie_root_equal = tie_root_equal_; s->tie_same_as_prev = tie_same_as_prev_;
 }
 
 }  // namespace shred

@@ -25,6 +25,7 @@ class TrainerCore {
   void count_bigrams();
   void init();
   int merge_batch(int batch_size);
+  int merge_loop(int batch_size);
   int train();
   void save(const char* model_path, const char* vocab_path);
   void get_stats(shred_stats_t* out);
@@ -59,6 +60,7 @@ class TrainerCore {
   Symbol placeholder_;
   // statistics of the last load/train
   uint64_t occurrences_ = 0, merges_last_ = 0, corpus_bytes_ = 0;
+  uint64_t tie_root_equal_ = 0, tie_same_as_prev_ = 0, last_merge_freq_ = ~0ull;
   double load_wall_ms_ = 0, train_wall_ms_ = 0, train_device_ms_ = 0, host_heap_ms_ = 0, save_wall_ms_ = 0;
   bool log_merges_ = false, quiet_ = false;
 };

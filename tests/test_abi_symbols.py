@@ -47,7 +47,14 @@ def test_struct_layouts_match_reference(native):
     assert ctypes.sizeof(cbase.BPEConfig) == 24 and ctypes.sizeof(cbase.BPEHeapEntry) == 24
     T = cbase.Trainer
     assert (T.heap.offset, T.corpus.offset, T.bigram_map.offset, T.num_merges.offset, T.merge_ops.offset, T.impl.offset) == (24, 48, 72, 96, 104, 128)
-    assert ctypes.sizeof(cbase.Stats) == 13 * 8 + 10 * 8 + 9 * 8 + 7 * 8 + 2 * 8
+    # the ctypes mirrors of the extension structs have the C compiler's sizes
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "sz.c")
+        open(src, "w").write('#include <stdio.h>\n#include "shred_abi.h"\nint main(void){printf("%zu %zu\\n", sizeof(shred_stats_t), sizeof(shred_encode_stats_t));return 0;}\n')
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "sz"), src], check=True)
+        c_stats, c_enc = map(int, subprocess.run([os.path.join(d, "sz")], check=True, capture_output=True, text=True).stdout.split())
+    assert ctypes.sizeof(cbase.Stats) == c_stats and ctypes.sizeof(cbase.EncodeStats) == c_enc
 
 
 def test_fails_loudly_without_gpu(native):
