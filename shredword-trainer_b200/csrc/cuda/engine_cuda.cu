@@ -576,7 +576,7 @@ class CudaEngine : public Engine {
   }
 
   // --------------------------------------------------------------------------------------------------------- merge
-  int merge(int32_t a, int32_t b, int32_t new_id, const Rec** recs, size_t* n, uint64_t* occurrences) override {
+  int merge(int32_t a, int32_t b, int32_t new_id, uint32_t /*serial*/, uint32_t /*list_len*/, const Rec** recs, size_t* n, uint64_t* occurrences) override {
     *recs = recs_; *n = 0; *occurrences = 0;
     const double tm0 = now_ms();
     CK(cudaSetDevice(dev_));  // the caller's thread may have another current device

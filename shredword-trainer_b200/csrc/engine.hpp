@@ -25,6 +25,12 @@ struct Rec {
 };
 enum : uint32_t { REC_PUSH = 0, REC_DEMOTE = 1, REC_PHANTOM = 2 };
 constexpr uint32_t REC_NO_SERIAL = 0xFFFFFFFFu;
+// Rec.kind carries, above its two kind bits, the length of the occurrence list the device created for the key in this very
+// pass (0 when the key already existed: a pair's occurrences are all created by one pass, afterwards they only disappear).
+constexpr uint32_t REC_KIND_MASK = 3u, REC_LEN_SHIFT = 2u, REC_LEN_MAX = 0x3FFFFFFFu;
+inline uint32_t rec_kind(uint32_t k) { return k & REC_KIND_MASK; }
+inline uint32_t rec_list_len(uint32_t k) { return k >> REC_LEN_SHIFT; }
+inline uint32_t rec_pack(uint32_t kind, uint64_t list_len) { return kind | (static_cast<uint32_t>(list_len < REC_LEN_MAX ? list_len : REC_LEN_MAX) << REC_LEN_SHIFT); }
 
 struct EngineConfig {
   int32_t unk_id;
@@ -66,7 +72,9 @@ class Engine {
   // Reset the pair table, count all adjacent non-unk pairs; *recs = PUSH records for entries with freq >= min.
   virtual int count_pairs(const Rec** recs, size_t* n) = 0;
   // Rewrite every leftmost non-overlapping (a,b) -> new_id, update the pair table, return the touched keys.
-  virtual int merge(int32_t a, int32_t b, int32_t new_id, const Rec** recs, size_t* n, uint64_t* occurrences) = 0;
+  // serial / list_len: the pair's dense id and the length of its occurrence list, both as reported by the PUSH record that
+  // created its heap entry (rec_list_len()); they let the device find the list with one load and size its grid.
+  virtual int merge(int32_t a, int32_t b, int32_t new_id, uint32_t serial, uint32_t list_len, const Rec** recs, size_t* n, uint64_t* occurrences) = 0;
   // freq[id] += word_count over all live symbols with 0 <= id < n_tokens (reference bpe.cpp:409-415).
   virtual int token_freqs(uint64_t* freq, size_t n_tokens) = 0;
   virtual int word_counts(uint64_t* out) = 0;  // host mirror of Corpus.word_counts

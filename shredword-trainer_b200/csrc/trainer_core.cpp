@@ -183,7 +183,11 @@ void TrainerCore::count_bigrams() {
     if (bx != by) return bx < by;
     return x.seq < y.seq;
   });
-  for (const Rec& r : order_) { ver_of(r.serial, r.key) = 0; heap_.push(unpack_key(r.key), r.val, 0, r.serial); }
+  for (const Rec& r : order_) {
+    ver_of(r.serial, r.key) = 0;
+    if (r.serial != REC_NO_SERIAL) meta_of(r.serial).list_len = rec_list_len(r.kind);
+    heap_.push(unpack_key(r.key), r.val, 0, r.serial);
+  }
   if (!quiet_) std::printf("[INFO]\t Added %zu pairs to heap (freq >= %llu)\n", n, static_cast<unsigned long long>(abi_->config.min_pair_freq));
   sync_mirrors();
 }
@@ -227,8 +231,9 @@ void TrainerCore::apply_records(const Rec* recs, size_t n) {
   for (const uint32_t ri : order_idx_) {
     const Rec& r = recs[ri];
     PairKey pk = unpack_key(r.key);
-    switch (r.kind) {
+    switch (rec_kind(r.kind)) {
       case REC_PUSH: {  // bpe.cpp:308-311
+        if (rec_list_len(r.kind) && r.serial != REC_NO_SERIAL) meta_of(r.serial).list_len = rec_list_len(r.kind);  // the pass that created the pair
         uint32_t v = ++ver_of(r.serial, r.key);
         heap_.push(pk, r.val, v, r.serial);
         break;
@@ -270,7 +275,7 @@ int TrainerCore::merge_loop(int batch_size) {
     HeapEnt top = heap_.pop();
     const uint64_t k = pack_key(top.key.first, top.key.second);
     uint32_t cur;
-    if (top.serial == REC_NO_SERIAL) { uint32_t* vp = version_.find(k); cur = vp ? *vp : 0; } else cur = top.serial < ver_.size() ? ver_[top.serial] : 0;
+    if (top.serial == REC_NO_SERIAL) { uint32_t* vp = version_.find(k); cur = vp ? *vp : 0; } else cur = top.serial < ver_.size() ? ver_[top.serial].ver : 0;
     if (top.version != cur) continue;  // stale, bpe.cpp:247-250
     if (is_phantom(top.key.first, top.key.second)) {  // recompute_freq == 0, bpe.cpp:53,252-257
       uint64_t* f = phantom_.find(k);
@@ -288,7 +293,8 @@ int TrainerCore::merge_loop(int batch_size) {
     const int32_t new_id = static_cast<int32_t>(256 + abi_->num_merges);  // bpe.cpp:259
     if (abi_->num_merges < merge_cap_) abi_->merge_ops[abi_->num_merges] = top.key;  // bpe.cpp:261
     const Rec* recs = nullptr; size_t n = 0; uint64_t occ = 0;
-    if (eng_->merge(top.key.first, top.key.second, new_id, &recs, &n, &occ) != 0) {
+    const uint32_t list_len = top.serial != REC_NO_SERIAL && top.serial < ver_.size() ? ver_[top.serial].list_len : 0;
+    if (eng_->merge(top.key.first, top.key.second, new_id, top.serial, list_len, &recs, &n, &occ) != 0) {
       std::fprintf(stderr, "[ERROR]\t device merge failed\n");
       sync_mirrors();
       return -1;

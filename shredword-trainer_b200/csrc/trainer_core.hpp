@@ -44,11 +44,15 @@ class TrainerCore {
   Engine* eng_;
   ExactHeap heap_;
   FlatMap<uint32_t> version_;   // PHANTOM pair key -> current version (absent = 0); phantoms have no device serial
-  HugeArray<uint32_t> ver_;     // pair serial -> current version (dense, no hashing on the replay path)
-  uint32_t& ver_of(uint32_t serial, uint64_t key) {
-    if (serial == REC_NO_SERIAL) return version_[key];
+  struct PairMeta { uint32_t ver, list_len; };  // list_len: entries of the pair's occurrence list on the device (engine.hpp rec_list_len)
+  HugeArray<PairMeta> ver_;     // pair serial -> current version + list length (dense, no hashing on the replay path)
+  PairMeta& meta_of(uint32_t serial) {
     if (serial >= ver_.size()) ver_.ensure(std::max<size_t>(serial + 1, ver_.size() * 2 + 1024));
     return ver_[serial];
+  }
+  uint32_t& ver_of(uint32_t serial, uint64_t key) {
+    if (serial == REC_NO_SERIAL) return version_[key];
+    return meta_of(serial).ver;
   }
   FlatMap<uint64_t> phantom_;   // pair keys containing unk_id -> freq as the reference's table would hold it
   std::vector<Rec> order_;      // scratch: records in application order

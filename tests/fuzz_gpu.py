@@ -11,7 +11,7 @@ os.environ.setdefault("SHRED_QUIET", "1")
 
 from corpora import SM, random_config, random_corpus  # noqa: E402
 from oracle_lib import Oracle  # noqa: E402
-from shredword import BPETrainer  # noqa: E402
+BPETrainer = None  # bound in main(): importing the CUDA binding is deferred so that tests/fuzz_cpu.py can reuse spicy_corpus
 
 
 def spicy_corpus(seed):
@@ -34,6 +34,7 @@ def spicy_corpus(seed):
 
 
 def main():
+    from shredword import BPETrainer
     first, n = int(sys.argv[1]), int(sys.argv[2])
     bad = 0
     for seed in range(first, first + n):

@@ -130,7 +130,7 @@ class HostSimEngine : public Engine {
     return 0;
   }
 
-  int merge(int32_t A, int32_t B, int32_t N, const Rec** recs, size_t* n, uint64_t* occurrences) override {
+  int merge(int32_t A, int32_t B, int32_t N, uint32_t /*serial*/, uint32_t /*list_len*/, const Rec** recs, size_t* n, uint64_t* occurrences) override {
     std::unordered_map<uint64_t, std::pair<int64_t, uint64_t>> agg;
     auto add = [&](uint64_t k, int64_t d, uint64_t seq) {
       seq |= seq_base(rank_);
@@ -226,7 +226,12 @@ class HostSimEngine : public Engine {
 };
 }  // namespace
 
-Engine* make_device_engine() { return new HostSimEngine(); }
+Engine* make_listsim_engine();  // engine_listsim.cpp
+Engine* make_device_engine() {
+  const char* e = std::getenv("SHRED_HOSTSIM_ENGINE");
+  if (e && std::string(e) == "lists") return make_listsim_engine();
+  return new HostSimEngine();
+}
 
 }  // namespace shred
 

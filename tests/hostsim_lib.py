@@ -10,8 +10,8 @@ HS_SO = os.path.join(HS_DIR, "_build", "libtrainer_hostsim.so")
 
 
 def build_hostsim():
-    srcs = [os.path.join(CSRC, "abi.cpp"), os.path.join(CSRC, "trainer_core.cpp"), os.path.join(HS_DIR, "engine_hostsim.cpp")]
-    deps = srcs + [os.path.join(HS_DIR, "engine_hostsim.cpp")] + [os.path.join(CSRC, h) for h in ("engine.hpp", "trainer_core.hpp", "exact_heap.hpp", "flat_map.hpp", "charset.hpp", "shard.hpp")]
+    srcs = [os.path.join(CSRC, "abi.cpp"), os.path.join(CSRC, "trainer_core.cpp"), os.path.join(HS_DIR, "engine_hostsim.cpp"), os.path.join(HS_DIR, "engine_listsim.cpp")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("engine.hpp", "trainer_core.hpp", "exact_heap.hpp", "flat_map.hpp", "charset.hpp", "shard.hpp", "layout.hpp")]
     if os.path.exists(HS_SO) and all(os.path.getmtime(d) <= os.path.getmtime(HS_SO) for d in deps):
         return HS_SO
     os.makedirs(os.path.dirname(HS_SO), exist_ok=True)

@@ -48,8 +48,16 @@ def _merges(t):
     return [(t.contents.merge_ops[i].a, t.contents.merge_ops[i].b, 256 + i) for i in range(n)]
 
 
+@pytest.fixture(params=["naive", "lists"])
+def engine(request, monkeypatch):
+    """naive: per-word vectors rewritten by a left-to-right pass.  lists: the CUDA engine's data structures (position-stable
+    symbol array, lazily validated per-pair occurrence lists) walked sequentially through csrc/layout.hpp."""
+    monkeypatch.setenv("SHRED_HOSTSIM_ENGINE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("case", GOLDEN, ids=case_ids())
-def test_host_logic_matches_reference(case, hs, tmp_path):
+def test_host_logic_matches_reference(case, hs, tmp_path, engine):
     import struct
     data = corpus_bytes(case)
     vs, unk, cov, mf = case["config"]
@@ -68,7 +76,7 @@ def test_host_logic_matches_reference(case, hs, tmp_path):
 
 
 @pytest.mark.parametrize("case", [c for c in SMALL if c["name"] in ("kat_py", "kat_cpp", "rnd003", "rnd017", "multi600k_1", "zipf2m_1")], ids=lambda c: c["name"])
-def test_heap_array_identical_stepwise(case, hs):
+def test_heap_array_identical_stepwise(case, hs, engine):
     """After bpe_init and after every single merge the replay heap (pairs and frequencies, array order) equals the
     reference-order heap of the oracle.  Versions may differ (the host bumps them on demotion), so they are not compared."""
     data = corpus_bytes(case)
