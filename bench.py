@@ -436,10 +436,11 @@ def main():
                    "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
                    "tie_rate_upper": st["tie_root_equal"] / merges if merges else None, "tie_rate_lower": st["tie_same_as_prev"] / merges if merges else None,
                    "tie_note": "SURVEY A15: share of merges whose frequency equals that of the entry left at the heap root (upper bound on a tied maximum) / the previous merge's frequency (lower bound)",
-                   "compactions": int(st["compactions"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
+                   "list_entries_probed": int(st["list_entries"]), "pool_entries": int(st["pool_entries"]), "train_device_ms_per_step": train_dev_ms / args.steps, "host_heap_ms": st["host_heap_ms"], "wait_ms": st["wait_ms"], "launch_ms": st["launch_ms"],
                    "ingest_device_ms": st["ingest_device_ms"], "ingest_gbs": st["ingest_bytes"] / (st["ingest_device_ms"] * 1e-3) / 1e9 if st["ingest_device_ms"] else None,
                    "count_device_ms": st["count_device_ms"], "count_gbs": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 if st["count_device_ms"] else None,
                    "count_frac_of_hbm_peak": st["count_bytes"] / (st["count_device_ms"] * 1e-3) / 1e9 / peak if st["count_device_ms"] and peak else None,
+                   "list_fill_device_ms": st["fill_device_ms"], "list_fill_gbs": st["fill_bytes"] / (st["fill_device_ms"] * 1e-3) / 1e9 if st["fill_device_ms"] else None,
                    "h2d_ms": st["h2d_ms"], "load_s_steps": [round(x["load_s"], 4) for x in steps], "train_s_steps": [round(x["train_s"], 4) for x in steps],
                    "save_s_steps": [round(x["save_s"], 4) for x in steps], "merges_md5": merges_md5, "vocab_md5": vocab_md5,
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},

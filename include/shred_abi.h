@@ -101,20 +101,22 @@ SHRED_API int bpe_b200_load_buffer(Trainer* trainer, const uint8_t* text, size_t
 typedef struct shred_stats_t {
   uint64_t n_words, n_symbols_initial, n_symbols_live, n_slots, n_tokens, corpus_bytes;
   uint64_t pair_entries, heap_size, heap_pushes, heap_pops;
-  uint64_t merges, occurrences, compactions;
-  uint64_t scan_launches;        /* merge-scan kernel launches in the last train */
+  uint64_t merges, occurrences;
+  uint64_t list_entries;         /* occurrence-list entries probed by all merges of the last train (occurrences of them were live) */
+  uint64_t pool_entries;         /* occurrence-list entries allocated so far (initial lists + lists of the pairs merges created) */
+  uint64_t scan_launches;        /* TIMED per-merge kernel launches in the last train (every SHRED_TIMING-th) */
   double scan_device_ms;         /* sum of their CUDA-event durations */
-  double scan_bytes;             /* algorithmic bytes they covered: sum 4*(slots scanned) */
-  uint64_t count_launches; double count_device_ms; double count_bytes;
+  double scan_bytes;             /* algorithmic bytes of the scan formulation they stand for: sum 4*(live symbols + words), SURVEY 8d */
+  uint64_t count_launches; double count_device_ms; double count_bytes;   /* k_count: CUDA events, 4S + 12N */
+  double fill_device_ms, fill_bytes;                                     /* fold + k_fill_lists: the initial occurrence lists */
   uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;
   uint64_t kernel_launches;      /* every kernel launch since create */
   double load_wall_ms, h2d_ms, train_wall_ms, host_heap_ms, wait_ms, save_wall_ms;
   double train_device_ms;        /* CUDA-event time of the last bpe_train on the engine's stream */
   double launch_ms;              /* host time spent issuing the per-merge kernel launches */
-  double scan_bytes_touched;     /* bytes of the symbol array the timed scans actually read (candidate tiles) */
-  uint64_t dense_launches; double dense_device_ms; double dense_bytes; /* timed scans that streamed >= 90 % of the array */
-  uint64_t cand_tiles, tiles_total; /* candidate / total tiles summed over all merges of the last train */
-  double scan_phase_ms, dense_phase_ms; /* in-kernel timer: start -> end of the scan phase, all / dense timed launches */
+  double scan_bytes_touched;     /* estimate of the bytes the timed launches really touch (list entries, probes, scratch, rewrites) */
+  uint64_t dense_launches; double dense_device_ms; double dense_bytes; /* timed launches with >= 65536 list entries */
+  double scan_phase_ms, dense_phase_ms; /* in-kernel timer: kernel start -> end of phase 1 (probe + deltas), all / dense timed launches */
   uint64_t h2d_bytes, d2h_bytes;
   /* tie statistics of the last train: merges whose frequency equals that of the entry left at the heap
    * root (upper bound on "another pair shares the maximum") / equals the previous merge's frequency (lower bound) */

@@ -38,7 +38,7 @@ def build(force=False, verbose_ptxas=False):
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     srcs = [os.path.join(CSRC, "abi.cpp"), os.path.join(CSRC, "trainer_core.cpp"), os.path.join(CSRC, "cuda", "engine_cuda.cu"), os.path.join(CSRC, "cuda", "encoder_cuda.cu")]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("engine.hpp", "trainer_core.hpp", "exact_heap.hpp", "flat_map.hpp", "charset.hpp", "shard.hpp")] + \
+    deps = srcs + [os.path.join(CSRC, h) for h in ("engine.hpp", "trainer_core.hpp", "exact_heap.hpp", "flat_map.hpp", "charset.hpp", "shard.hpp", "layout.hpp")] + \
         [os.path.join(CSRC, "cuda", h) for h in ("common.cuh", "kernels_tokenize.cuh", "kernels_scan.cuh", "kernels_ingest.cuh", "kernels_count.cuh", "kernels_fold.cuh", "kernels_dist.cuh", "kernels_merge.cuh", "kernels_encode.cuh")] + \
         [os.path.join(ROOT, "include", "shred_abi.h")]
     if force or _stale(LIB, deps):

@@ -19,63 +19,75 @@
 
 typedef unsigned long long ull;
 
-constexpr int32_t DEAD = -1;
-constexpr uint32_t HDR_BIT = 0x80000000u;
-constexpr int32_t UNK_CODE_NEG = 0x7FFFFFFF;  // stored code of unk symbols when unk_id < 0
+using lay::DEAD;
+using lay::UNK_CODE_NEG;
+using lay::Params;
+using lay::code_to_id;
+using lay::fc_key;
+constexpr uint32_t HDR_BIT = lay::HDR_TAG;
+constexpr uint32_t NONE32 = lay::NONE32;
 constexpr uint64_t PT_EMPTY = ~0ull;
 constexpr uint64_t SEQ_MAX = ~0ull;
+constexpr uint64_t NO_LIST = ~0ull;
 constexpr int N_SM_FALLBACK = 148;
 
 enum : uint32_t { ERR_DT_FULL = 1, ERR_PT_FULL = 2, ERR_WT_FULL = 4, ERR_WT_COLLISION = 8, ERR_REC_FULL = 16, ERR_HAS_NUL = 32, ERR_BARRIER = 64,
-                  ERR_PEER_TIMEOUT = 128, ERR_INBOX_FULL = 256 };
+                  ERR_PEER_TIMEOUT = 128, ERR_INBOX_FULL = 256, ERR_POOL_FULL = 512, ERR_SCRATCH_FULL = 1024, ERR_BAD_LIST = 2048 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
   return x;
 }
 __device__ __forceinline__ bool is_delim(uint32_t c) { return c <= 32u && ((0x100002600ull >> c) & 1ull); }  // \t \n \r space
-__device__ __forceinline__ uint64_t fc_key(int32_t a, int32_t b) {  // bpe.cpp:277-278: both operands sign-extend
-  return (static_cast<uint64_t>(static_cast<int64_t>(a)) << 32) | static_cast<uint64_t>(static_cast<int64_t>(b));
-}
 
-struct Ctrl {  // mapped pinned host memory, written by finalize_block
+struct Ctrl {  // mapped pinned host memory, written by the CTA that publishes a pass
   volatile uint64_t flag;
-  uint64_t n_recs, occ, occ_local, pt_n, n_leaders, n_keys, cand_tiles;
+  uint64_t n_recs, occ, occ_local, pt_n, n_keys, list_len, pool_top;
   uint32_t err, pad;
 };
 
-struct DevCounters {  // device memory
-  uint32_t wl_n, dt_n, rec_n, blocks_done;
-  ull occ;
+// Device counters.  The per-pass counters exist twice: pass number e uses [e & 1] and zeroes [(e + 1) & 1] for its successor
+// (the successor is a later launch on the same stream), so no pass ends with a "last CTA re-arms" step.
+struct DevCounters {
+  uint32_t n_occ[2], dt_n[2], rec_n[2];
+  uint32_t bar, err;
   ull pt_n;
-  uint32_t err, pad;
+  ull pool_top;
   ull n_tokens;
-  uint32_t n_unique, blocks_done2;
-  uint32_t cand_tiles, bar;
-  uint32_t sent_ctas, pad4;
+  uint32_t n_unique, sent_ctas;
+  ull sent_epoch;  // multi-GPU: number of the last exchange all of whose local CTAs have sent (and so have read their list length)
 };
 
 struct DeltaTable {
-  uint64_t* keys; ull* delta; ull* seq; uint32_t* list; uint64_t* klist;  // list/klist: slot and key of every used slot, dense
+  uint64_t* keys; ull* delta; ull* seq;
+  uint32_t* nocc;  // occurrences that will enter the key's list (unweighted); doubles as the rank dispenser
+  ull* base;       // start of the key's list in the pool, written by the fold (NO_LIST: the key gets none)
+  uint32_t* list; uint64_t* klist;  // slot and key of every used slot, dense
+  uint32_t* n;     // -> DevCounters::dt_n[parity] of the running pass
   uint64_t mask; uint64_t empty; uint32_t cap;
 };
 struct PairEnt { uint64_t key; uint64_t freq; };  // one 16-byte load fetches both
+// Occurrence list of a pair: positions (slot of the pair's first token) in pool[off, off + len), created by ONE pass -- the
+// count pass, or the merge that created the younger of the two tokens -- and only ever validated lazily afterwards.
+struct ListRef { ull off; uint32_t len; uint32_t fill; };
 struct PairTable {
   PairEnt* ent;
   uint32_t* serial;  // dense id per entry = number of entries that existed when it was created (the host indexes by it)
-  uint64_t mask; uint64_t cap;
+  ListRef* lists;    // indexed by serial (survives rehashing)
+  uint64_t mask; uint64_t cap; uint64_t lists_cap;
 };
 
 // ------------------------------------------------------------------------------------------------ hash-table helpers
 
-__device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, uint64_t key, int64_t delta, uint64_t seq) {
+// Adds (delta, seq) to `key`, claiming a slot if the key is new; returns the slot (NONE32 if the table is full).
+__device__ __forceinline__ uint32_t dt_add(const DeltaTable& dt, DevCounters* ctr, uint64_t key, int64_t delta, uint64_t seq) {
   uint64_t slot = mix64(key) & dt.mask;
   for (uint32_t probe = 0; probe < dt.cap; ++probe) {
     uint64_t cur = dt.keys[slot];
     if (cur == dt.empty) {
       uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot]), static_cast<ull>(dt.empty), static_cast<ull>(key));
       if (prev == dt.empty) {
-        uint32_t idx = atomicAdd(&ctr->dt_n, 1u);
+        uint32_t idx = atomicAdd(dt.n, 1u);
         if (idx < dt.cap) { dt.list[idx] = static_cast<uint32_t>(slot); dt.klist[idx] = key; }
         cur = key;
       } else cur = prev;
@@ -83,21 +95,23 @@ __device__ __forceinline__ void dt_add(const DeltaTable& dt, DevCounters* ctr, u
     if (cur == key) {
       atomicAdd(&dt.delta[slot], static_cast<ull>(delta));
       atomicMin(&dt.seq[slot], static_cast<ull>(seq));
-      return;
+      return static_cast<uint32_t>(slot);
     }
     slot = (slot + 1) & dt.mask;
   }
   atomicOr(&ctr->err, ERR_DT_FULL);
+  return NONE32;
 }
 
 // The four delta-table updates of one occurrence with their memory round trips overlapped (each update alone is a chain
 // load -> CAS -> list reservation of ~0.5 us links): home-slot loads together, claims together, one list reservation
 // for all newly claimed keys.  A key whose home slot holds another key falls back to the probing dt_add.
+// slot_out[j] = the key's slot (NONE32 for an invalid j or a full table).
 __device__ __forceinline__ void dt_add4(const DeltaTable& dt, DevCounters* ctr, const uint64_t (&key)[4], const int64_t (&delta)[4], const uint64_t (&seq)[4],
-                                        uint32_t valid) {
+                                        uint32_t valid, uint32_t (&slot_out)[4]) {
   uint64_t slot[4], cur[4], prev[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) { slot[j] = mix64(key[j]) & dt.mask; cur[j] = (valid >> j) & 1u ? dt.keys[slot[j]] : 0ull; }
+  for (int j = 0; j < 4; j++) { slot[j] = mix64(key[j]) & dt.mask; cur[j] = (valid >> j) & 1u ? dt.keys[slot[j]] : 0ull; slot_out[j] = NONE32; }
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     prev[j] = cur[j];
@@ -110,7 +124,7 @@ __device__ __forceinline__ void dt_add4(const DeltaTable& dt, DevCounters* ctr, 
     if (prev[j] == dt.empty) { claimed |= 1u << j; cur[j] = key[j]; } else cur[j] = prev[j];
   }
   if (claimed) {
-    uint32_t idx = atomicAdd(&ctr->dt_n, static_cast<uint32_t>(__popc(claimed)));
+    uint32_t idx = atomicAdd(dt.n, static_cast<uint32_t>(__popc(claimed)));
 #pragma unroll
     for (int j = 0; j < 4; j++) if ((claimed >> j) & 1u) {
       if (idx < dt.cap) { dt.list[idx] = static_cast<uint32_t>(slot[j]); dt.klist[idx] = key[j]; }
@@ -122,7 +136,8 @@ __device__ __forceinline__ void dt_add4(const DeltaTable& dt, DevCounters* ctr, 
     if (cur[j] == key[j]) {
       atomicAdd(&dt.delta[slot[j]], static_cast<ull>(delta[j]));
       atomicMin(&dt.seq[slot[j]], static_cast<ull>(seq[j]));
-    } else dt_add(dt, ctr, key[j], delta[j], seq[j]);
+      slot_out[j] = static_cast<uint32_t>(slot[j]);
+    } else slot_out[j] = dt_add(dt, ctr, key[j], delta[j], seq[j]);
   }
 }
 

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../../include/shred_abi.h"
+#include "../layout.hpp"
 
 namespace shred {
 namespace {

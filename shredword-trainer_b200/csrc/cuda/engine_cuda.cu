@@ -3,16 +3,16 @@
 // This file holds the host side (buffers, launches, multi-GPU rendezvous); the kernels live in the .cuh fragments
 // included below.
 //
-// Data layout in HBM
-//   ids[]   int32, one flat array holding every unique word back to back in reference word order (A3):
-//             [HDR|wi] s0 s1 ... s(len-1) [DEAD ...]          HDR|wi < -1, symbols >= 0, DEAD == -1
-//           A word keeps its slot range between compactions; merges left-pack its live symbols and fill the tail with
-//           DEAD.  Because words are stored in reference scan order, "flat position" is monotone in the reference's
-//           (word index, position) order and serves as the sequence number the host needs (Appendix A14).
-//   wid[]   uint32 word index per slot; wcnt[] uint64 word counts, woff[] uint64 slot offsets (N+1), wlen[] uint32 lengths
-//   planes  tile occurrence index (one bit plane per token id; a merge scans only tiles holding both tokens)
-//   pair table   open addressing, uint64 key (first<<32|second) -> uint64 freq + serial  (reference BIMap, hash.cpp:104-130)
-//   delta table  open addressing scratch, key -> (sum of +/-count, min sequence)         (reference FreqChangeMap, bpe.cpp:9-38)
+// Data layout in HBM (csrc/layout.hpp has the encoding and the per-occurrence logic, shared with a CPU walk-through in tests/)
+//   ids[]   int32, position-stable: every unique word owns a fixed slot range [HDR|wi] b0 b1 ... (one slot per byte), words back
+//           to back in reference word order (A3).  A token lives at the slot of its first byte and never moves; a merged token
+//           marks its second and last slot with SKIP(length).  Flat position is monotone in the reference's (word, position)
+//           scan order: it is the sequence number the host needs (Appendix A14) and what the occurrence lists store.
+//   wid[]   uint32 word index per slot; wcnt[] uint64 word counts; woff[] uint64 slot offsets (N+1)
+//   pool[]  uint32 occurrence lists: for every pair that can reach the heap, the slots where it occurred when it was created
+//           (by the count pass or by the one merge that created its younger token); validated lazily, never updated
+//   pair table   open addressing, uint64 key (first<<32|second) -> uint64 freq + serial; lists[serial] = {offset, length}
+//   delta table  open addressing scratch, key -> (sum of +/-count, min sequence, occurrences)  (reference FreqChangeMap, bpe.cpp:9-38)
 //
 // Kernels (reference loop each one replaces)                                               file
 //   k_tokenize ........ bpe.cpp:131-153 + hash.cpp:29-53   tokenise, unique-word table     kernels_tokenize.cuh
@@ -20,10 +20,11 @@
 //   k_scatter/k_sort_buckets  hash.cpp:61-72               word order (djb2 & 4095, first)  kernels_ingest.cuh
 //   k_symbolize ....... histogram.cpp:7-27                 bytes -> ids, unk substitution   kernels_ingest.cuh
 //   k_count ........... bpe.cpp:187-218                    adjacent pair counts             kernels_count.cuh
-//   k_finalize_count .. bpe.cpp:219-227                    fold counts, seed records        kernels_fold.cuh
+//   k_finalize_count .. bpe.cpp:219-227                    fold counts, seed records, reserve lists   kernels_fold.cuh
+//   k_fill_lists ...... (no counterpart)                   initial occurrence lists         kernels_count.cuh
 //   k_merge ........... bpe.cpp:265-318                    one cooperative launch per merge kernels_merge.cuh
-//                       scan of the candidate tiles with per-occurrence count deltas | grid barrier | deltas folded
-//                       into the pair table + records published | in-place rewrite of the touched words
+//                       probe the pair's occurrence list, per-occurrence count deltas | grid barrier | deltas folded into the
+//                       pair table + records published | grid barrier | in-place rewrite (4 stores per occurrence) + new lists
 //   exchange_deltas ... (multi-GPU) per-merge delta exchange over NVLink peer memory        kernels_dist.cuh
 //   k_token_freq ...... bpe.cpp:409-415                    final token frequencies          kernels_merge.cuh
 #include <cuda_profiler_api.h>
@@ -46,6 +47,7 @@
 #include "../../../include/shred_abi.h"
 #include "../charset.hpp"
 #include "../engine.hpp"
+#include "../layout.hpp"
 #include "../shard.hpp"
 
 namespace shred {
@@ -96,20 +98,20 @@ class CudaEngine : public Engine {
       dbg_print_ = d && *d && *d != '0';
     }
     CK(cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SORT_CAP * sizeof(ull))));
+    CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(CountStage))));
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4, false>, 256, 0) == cudaSuccess && nb > 0) scan_ctas_per_sm_ = nb;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
     if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
     if (world_ > 1) {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<4, true>, 256, 0) == cudaSuccess && nb > 0 && nb < scan_ctas_per_sm_) scan_ctas_per_sm_ = nb;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<true>, 256, 0) == cudaSuccess && nb > 0 && nb < merge_ctas_per_sm_) merge_ctas_per_sm_ = nb;
       const char* r = std::getenv("SHRED_RANK");
       rank_ = r ? std::atoi(r) : 0;
       if (world_ > MAX_RANKS || rank_ < 0 || rank_ >= world_) { std::fprintf(stderr, "[ERROR]\t bad SHRED_RANK/SHRED_WORLD (%d/%d, at most %d ranks)\n", rank_, world_, MAX_RANKS); return -1; }
       RC(dist_setup());
     } else { world_ = 1; rank_ = 0; }
-    if (const char* pl = std::getenv("SHRED_PLAIN_LAUNCH")) plain_launch_ = *pl && *pl != '0';
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
-    if (const char* ho = std::getenv("SHRED_HOT_ON_OCC")) hot_on_occ_ = std::strtoull(ho, nullptr, 10);
+    if (const char* mg = std::getenv("SHRED_MERGE_GRID")) force_grid_ = std::atoi(mg);  // tests: fixed grid for every merge launch
     if (const char* pm = std::getenv("SHRED_PROFILE_MERGES")) {  // "0,1,2000": cudaProfilerStart/Stop around these merges (ncu --profile-from-start off)
       for (const char* q = pm; *q;) { char* end = nullptr; const unsigned long v = std::strtoul(q, &end, 10); if (end == q) break; profile_merges_.push_back(static_cast<uint32_t>(v)); q = *end ? end + 1 : end; }
     }
@@ -225,31 +227,6 @@ class CudaEngine : public Engine {
     return 0;
   }
 
-  // The tile index is the one GB-sized buffer whose size is close to the corpus text's: handing it back to the stream-ordered
-  // pool lets the pool give it to the next trainer's text buffer and then grow again for the next index (a ~1 s stall when
-  // it happens).  One spare per process is parked here instead.
-  struct PlaneCache { uint32_t* ptr = nullptr; uint64_t bytes = 0; int dev = -1; std::mutex mu; };
-  static PlaneCache& plane_cache() { static PlaneCache c; return c; }
-  int acquire_planes(uint64_t bytes) {
-    PlaneCache& c = plane_cache();
-    {
-      std::lock_guard<std::mutex> hold(c.mu);
-      if (c.ptr && c.dev == dev_ && c.bytes >= bytes && c.bytes <= bytes + bytes / 2) { planes_ = c.ptr; planes_bytes_ = c.bytes; c.ptr = nullptr; c.bytes = 0; return 0; }
-    }
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&planes_), bytes, st_));
-    planes_bytes_ = bytes;
-    return 0;
-  }
-  void release_planes() {
-    if (!planes_) return;
-    cudaStreamSynchronize(st_);  // nothing queued may still touch it
-    PlaneCache& c = plane_cache();
-    std::lock_guard<std::mutex> hold(c.mu);
-    if (!c.ptr) { c.ptr = planes_; c.bytes = planes_bytes_; c.dev = dev_; }
-    else cudaFreeAsync(planes_, st_);
-    planes_ = nullptr; planes_bytes_ = 0;
-  }
-
   // pinned staging ring shared by all trainers of the process (cudaHostAlloc is slow, so it is done once)
   static constexpr int STAGE_BUFS = 8;
   static constexpr size_t STAGE_BYTES = 16u << 20;
@@ -344,6 +321,7 @@ class CudaEngine : public Engine {
     uint32_t *u_slot = nullptr, *u_n = nullptr, *bcnt = nullptr, *bstart = nullptr, *cursor = nullptr, *tmp_slot = nullptr, *order_slot = nullptr;
     ull *tmp_first = nullptr, *d_hist = nullptr, *len1 = nullptr, *sums = nullptr;
     uint8_t* d_keep = nullptr;
+    uint32_t* wlen = nullptr;  // word lengths: only needed until the offsets exist
     const uint64_t Na = N ? N : 1;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&u_slot), Na * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&tmp_slot), Na * 4, st_));
     CK(cudaMallocAsync(reinterpret_cast<void**>(&order_slot), Na * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&tmp_first), Na * 8, st_));
@@ -355,12 +333,12 @@ class CudaEngine : public Engine {
     CK(cudaMallocAsync(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8, st_));
     auto free_tmp = [&]() {
       cudaFreeAsync(u_slot, st_); cudaFreeAsync(tmp_slot, st_); cudaFreeAsync(order_slot, st_); cudaFreeAsync(tmp_first, st_); cudaFreeAsync(len1, st_); cudaFreeAsync(u_n, st_); cudaFreeAsync(bcnt, st_);
-      cudaFreeAsync(bstart, st_); cudaFreeAsync(cursor, st_); cudaFreeAsync(d_hist, st_); cudaFreeAsync(d_keep, st_); cudaFreeAsync(sums, st_);
+      cudaFreeAsync(bstart, st_); cudaFreeAsync(cursor, st_); cudaFreeAsync(d_hist, st_); cudaFreeAsync(d_keep, st_); cudaFreeAsync(sums, st_); cudaFreeAsync(wlen, st_);
     };
     CK(cudaMemsetAsync(u_n, 0, 4, st_)); CK(cudaMemsetAsync(bcnt, 0, 4096 * 4, st_)); CK(cudaMemsetAsync(cursor, 0, 4096 * 4, st_));
     CK(cudaMemsetAsync(d_hist, 0, 256 * 8, st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&wcnt_), Na * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wlen_), Na * 4, st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&woff_[0]), (Na + 1) * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&woff_[1]), (Na + 1) * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wcnt_), Na * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wlen), Na * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&woff_), (Na + 1) * 8, st_));
     ull S1 = 0;  // total slots = symbols + headers
     if (N) {
       k_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, bcnt);
@@ -368,10 +346,10 @@ class CudaEngine : public Engine {
       k_scatter<<<grid_for(N, 256), 256, 0, st_>>>(wt, u_slot, N, bstart, cursor, tmp_slot, tmp_first);
       k_sort_buckets<<<4096, SORT_THREADS, SORT_CAP * sizeof(ull), st_>>>(tmp_slot, tmp_first, bstart, order_slot);
       k_rank_big<<<grid_for(N, 128), 128, 0, st_>>>(wt, tmp_slot, tmp_first, N, bstart, order_slot); launches_++;  // only buckets above SORT_CAP do work
-      k_hist_words<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, d_hist, wcnt_, wlen_, len1);
+      k_hist_words<<<grid_for(N, 256), 256, 0, st_>>>(d_text, wt, order_slot, N, d_hist, wcnt_, wlen, len1);
       k_scan_sums<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums);
       k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(sums, nb_scan, sums + nb_scan);
-      k_scan_apply<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums, woff_[0]);
+      k_scan_apply<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums, woff_);
       launches_ += 8; es_.ingest_launches += 8;
       CK(cudaMemcpyAsync(&S1, sums + nb_scan, 8, cudaMemcpyDeviceToHost, st_));
     }
@@ -385,7 +363,7 @@ class CudaEngine : public Engine {
     host_counts_.clear();
     if (world_ > 1 && N) {  // keep only this rank's contiguous range of words (shard.hpp); ingest itself is replicated
       std::vector<ull> hoff(static_cast<size_t>(N) + 1);
-      CK(cudaMemcpyAsync(hoff.data(), woff_[0], static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost, st_));
+      CK(cudaMemcpyAsync(hoff.data(), woff_, static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost, st_));
       host_counts_.resize(N);
       CK(cudaMemcpyAsync(host_counts_.data(), wcnt_, static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost, st_));
       CK(cudaStreamSynchronize(st_));
@@ -395,82 +373,39 @@ class CudaEngine : public Engine {
       n_local = hi - lo;
       const ull base_off = hoff[lo];
       S1 = hoff[hi] - base_off;
-      ull *wc = nullptr, *wo0 = nullptr, *wo1 = nullptr; uint32_t* wl = nullptr;
+      ull *wc = nullptr, *wo = nullptr;
       const uint64_t nl = n_local ? n_local : 1;
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&wc), nl * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wl), nl * 4, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&wo0), (nl + 1) * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wo1), (nl + 1) * 8, st_));
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wc), nl * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wo), (nl + 1) * 8, st_));
       if (n_local) {
         CK(cudaMemcpyAsync(wc, wcnt_ + lo, static_cast<uint64_t>(n_local) * 8, cudaMemcpyDeviceToDevice, st_));
-        CK(cudaMemcpyAsync(wl, wlen_ + lo, static_cast<uint64_t>(n_local) * 4, cudaMemcpyDeviceToDevice, st_));
-        k_rebase<<<grid_for(n_local, 256), 256, 0, st_>>>(woff_[0] + lo, n_local, base_off, wo0); launches_++;
+        k_rebase<<<grid_for(n_local, 256), 256, 0, st_>>>(woff_ + lo, n_local, base_off, wo); launches_++;
       }
-      cudaFreeAsync(wcnt_, st_); cudaFreeAsync(wlen_, st_); cudaFreeAsync(woff_[0], st_); cudaFreeAsync(woff_[1], st_);
-      wcnt_ = wc; wlen_ = wl; woff_[0] = wo0; woff_[1] = wo1;
+      cudaFreeAsync(wcnt_, st_); cudaFreeAsync(woff_, st_);
+      wcnt_ = wc; woff_ = wo;
       es_.d2h_bytes += static_cast<uint64_t>(N) * 16;
     }
     n_words_ = n_local;
     n_slots_ = S1; n_live_ = S1;
-    if (S1 + 64 >= (1ull << 32)) { free_tmp(); free_wt(); std::fprintf(stderr, "[ERROR]\t corpus needs more than 2^32 symbol slots on one GPU\n"); return -1; }
+    if (S1 + 64 >= (1ull << 32) || N >= lay::LOW30) { free_tmp(); free_wt(); std::fprintf(stderr, "[ERROR]\t corpus needs more than 2^32 symbol slots or 2^30 words on one GPU\n"); return -1; }
     ids_cap_ = ((S1 + 8 + 1023) / 1024) * 1024;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&ids_[0]), ids_cap_ * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&ids_[1]), ids_cap_ * 4, st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&wl_), ids_cap_ * 4, st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&wid_[0]), ids_cap_ * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wid_[1]), ids_cap_ * 4, st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&claimed_), Na * 4, st_));
-    CK(cudaMemsetAsync(claimed_, 0, Na * 4, st_));
-    CK(cudaMemsetAsync(wid_[0], 0, ids_cap_ * 4, st_)); CK(cudaMemsetAsync(wid_[1], 0, ids_cap_ * 4, st_));
-    merge_no_ = 0;
-    cur_ = 0;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&ids_), ids_cap_ * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wid_), ids_cap_ * 4, st_));
+    CK(cudaMemsetAsync(wid_, 0, ids_cap_ * 4, st_));
+    // occurrence lists: one entry per adjacent pair of the fresh corpus (< S1) + two per rewritten occurrence (< S1 - words)
+    pool_cap_ = S1 + 2 * (S1 - n_local) + 1024;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pool_), pool_cap_ * 4, st_));
     CK(cudaMemcpyAsync(d_keep, info->keep, 256, cudaMemcpyHostToDevice, st_));
-    CK(cudaMemcpyAsync(woff_[0] + n_local, &S1, 8, cudaMemcpyHostToDevice, st_));
-    if (n_local) { k_symbolize<<<grid_for(n_local, 256), 256, 0, st_>>>(d_text, wt, order_slot + lo, n_local, woff_[0], d_keep, P_.unk_code, ids_[0], wid_[0]); launches_++; es_.ingest_launches++; }
-    k_fill_i32<<<grid_for(ids_cap_ - S1, 256), 256, 0, st_>>>(ids_[0], S1, ids_cap_, DEAD); launches_++; es_.ingest_launches++;
+    CK(cudaMemcpyAsync(woff_ + n_local, &S1, 8, cudaMemcpyHostToDevice, st_));
+    if (n_local) { k_symbolize<<<grid_for(n_local, 256), 256, 0, st_>>>(d_text, wt, order_slot + lo, n_local, woff_, d_keep, P_.unk_code, ids_, wid_); launches_++; es_.ingest_launches++; }
+    k_fill_i32<<<grid_for(ids_cap_ - S1, 256), 256, 0, st_>>>(ids_, S1, ids_cap_, DEAD); launches_++; es_.ingest_launches++;
+    const int32_t terminator = lay::make_hdr(n_local);  // the last token of the last word has no right neighbour
+    CK(cudaMemcpyAsync(ids_ + S1, &terminator, 4, cudaMemcpyHostToDevice, st_));
     CK(cudaStreamSynchronize(st_));
     CK(cudaGetLastError());
     free_tmp(); free_wt();
-    RC(build_planes());
     // --- pair/delta tables sized for this trainer
     RC(alloc_tables());
     loaded_ = true;
-    return 0;
-  }
-
-  // (re)build the tile occurrence index for the current ids buffer
-  int build_planes() {
-    if (std::getenv("SHRED_NO_TILE_INDEX")) return 0;
-    const double tb0 = now_ms();
-    const uint32_t id_cap = static_cast<uint32_t>(256 + vocab_hint_ + 64);
-    // finest tiling whose bit planes fit the budget (a tile is at least one warp row = 128 slots)
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-    uint64_t budget = 6ull << 30;
-    if (const char* e = std::getenv("SHRED_TILE_INDEX_MB")) budget = static_cast<uint64_t>(std::atoll(e)) << 20;
-    if (budget > (free_b + (planes_ ? static_cast<uint64_t>(id_cap_) * plane_words_ * 4 : 0)) / 3) budget = (free_b + (planes_ ? static_cast<uint64_t>(id_cap_) * plane_words_ * 4 : 0)) / 3;
-    uint32_t shift = MIN_TILE_SHIFT, W = 0;
-    uint64_t bytes = 0;
-    for (;; ++shift) {
-      const uint32_t n_tiles_cap = static_cast<uint32_t>((ids_cap_ + (1ull << shift) - 1) >> shift);
-      W = (n_tiles_cap + 31) / 32;
-      bytes = static_cast<uint64_t>(id_cap) * W * 4;
-      if (bytes <= budget || shift == MAX_TILE_SHIFT) break;
-    }
-    if (bytes > budget) {  // even the coarsest tiling is too big: scan every tile
-      release_planes();
-      plane_words_ = 0; id_cap_ = 0; tile_shift_ = MAX_TILE_SHIFT;
-      return 0;
-    }
-    if (!planes_ || W != plane_words_ || id_cap != id_cap_ || shift != tile_shift_) {
-      release_planes();
-      RC(acquire_planes(bytes));
-      plane_words_ = W; id_cap_ = id_cap; tile_shift_ = shift;
-    }
-    CK(cudaMemsetAsync(planes_, 0, bytes, st_));
-    const double tb1 = now_ms();
-    if (n_slots_) { k_build_planes<<<grid_for(n_slots_, 256), 256, 0, st_>>>(ids_[cur_], n_slots_, planes_, plane_words_, id_cap_, tile_shift_); launches_++; }
-    if (dbg_print_) {
-      cudaStreamSynchronize(st_);
-      std::fprintf(stderr, "[PLANES]\t shift %u, %.1f MB: alloc+memset issue %.2f ms, build %.2f ms (free %.1f GB)\n", tile_shift_, bytes / 1048576.0, tb1 - tb0, now_ms() - tb1,
-                   free_b / 1073741824.0);
-    }
     return 0;
   }
 
@@ -480,32 +415,41 @@ class CudaEngine : public Engine {
       RC(alloc_dt(cap));
     }
     if (!pt_.ent) RC(alloc_pt(&pt_, 1ull << 20));
-    if (!recs_) {
-      rec_cap_ = dt_.cap;
-      CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped));
-    }
     return 0;
   }
   int alloc_dt(uint64_t cap) {
-    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); dt_.keys = nullptr; }
+    if (dt_.keys) {
+      cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.nocc, st_); cudaFreeAsync(dt_.base, st_);
+      cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); dt_.keys = nullptr;
+    }
     CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.keys), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.delta), cap * 8, st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.seq), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.list), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.seq), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.nocc), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.base), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.list), cap * 4, st_));
     CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.klist), cap * 8, st_));
     dt_.cap = static_cast<uint32_t>(cap); dt_.mask = cap - 1;
     // a key value no pair can produce: high word >= 2^31 that is neither all-ones nor unk_id
     uint32_t hi = 0x80000000u; if (static_cast<uint32_t>(cfg_.unk_id) == hi) hi = 0x80000001u;
     dt_.empty = static_cast<uint64_t>(hi) << 32;
     k_fill_u64<<<grid_for(cap, 256), 256, 0, st_>>>(reinterpret_cast<ull*>(dt_.keys), cap, dt_.empty);
-    CK(cudaMemsetAsync(dt_.delta, 0, cap * 8, st_)); CK(cudaMemsetAsync(dt_.seq, 0xFF, cap * 8, st_));
+    CK(cudaMemsetAsync(dt_.delta, 0, cap * 8, st_)); CK(cudaMemsetAsync(dt_.seq, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(dt_.nocc, 0, cap * 4, st_));
+    CK(cudaMemsetAsync(dt_.base, 0xFF, cap * 8, st_));
     launches_++;
-    if (recs_ && rec_cap_ < dt_.cap) { cudaFreeHost(recs_); recs_ = nullptr; rec_cap_ = dt_.cap; CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped)); }
+    // the record buffer holds at most one record per key of a pass; callers fetch recs_ only after the last possible growth
+    if (!recs_ || rec_cap_ < dt_.cap) {
+      if (recs_) { CK(cudaStreamSynchronize(st_)); cudaFreeHost(recs_); recs_ = nullptr; }
+      rec_cap_ = dt_.cap;
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped));
+    }
     return 0;
   }
   int alloc_pt(PairTable* pt, uint64_t cap) {
     CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->ent), cap * sizeof(PairEnt), st_));
     CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->serial), cap * 4, st_));
     pt->cap = cap; pt->mask = cap - 1;
+    pt->lists_cap = cap / 2 + 4096;  // the table stays at most half full, serials are dense
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->lists), pt->lists_cap * sizeof(ListRef), st_));
     CK(cudaMemsetAsync(pt->ent, 0xFF, cap * sizeof(PairEnt), st_));  // key = EMPTY; freq is written when the entry is claimed
+    CK(cudaMemsetAsync(pt->lists, 0, pt->lists_cap * sizeof(ListRef), st_));  // len 0 = the pair has no list
     return 0;
   }
   int grow_pt(uint64_t need_entries) {
@@ -514,9 +458,21 @@ class CudaEngine : public Engine {
     PairTable nt; std::memset(&nt, 0, sizeof nt);
     RC(alloc_pt(&nt, cap));
     k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
+    CK(cudaMemcpyAsync(nt.lists, pt_.lists, pt_.lists_cap * sizeof(ListRef), cudaMemcpyDeviceToDevice, st_));
     CK(cudaStreamSynchronize(st_));
-    cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_);
+    cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); cudaFreeAsync(pt_.lists, st_);
     pt_ = nt;
+    return 0;
+  }
+  int ensure_scratch(uint64_t n_entries) {  // one scratch entry per occurrence of a merge, at most one per list entry
+    if (n_entries <= sc_.cap) return 0;
+    uint64_t cap = sc_.cap ? sc_.cap : (1u << 16);
+    while (cap < n_entries) cap *= 2;
+    if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+    if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.a), cap * sizeof(uint4), st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.b), cap * sizeof(uint2), st_));
+    sc_.cap = static_cast<uint32_t>(cap);
     return 0;
   }
 
@@ -525,18 +481,20 @@ class CudaEngine : public Engine {
     CK(cudaSetDevice(dev_));
     *recs = recs_; *n = 0;
     if (!loaded_) return 0;
-    last_occ_ = ~0ull;  // a fresh pair table: the first merges are the occurrence-heavy ones
     for (int attempt = 0; attempt < 12; ++attempt) {
       CK(cudaMemsetAsync(pt_.ent, 0xFF, pt_.cap * sizeof(PairEnt), st_));
+      CK(cudaMemsetAsync(pt_.lists, 0, pt_.lists_cap * sizeof(ListRef), st_));
       CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
       bar_count_ = 0;
       pt_n_ = 0;
+      pass_ = 0;  // the count pass runs on parity 0 of the freshly zeroed counters; the first merge takes parity 1
+      dt_.n = &ctr_->dt_n[0];
       ++flag_;
       CK(cudaEventRecord(ev0_, st_));
+      const uint32_t n4c = static_cast<uint32_t>((n_slots_ + 3) / 4);
       if (n_words_) {
-        const uint32_t n4c = static_cast<uint32_t>((n_slots_ + 3) / 4);
-        k_count<<<n_sm_ * 4, 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_[cur_]), reinterpret_cast<const uint4*>(wid_[cur_]), n4c, wcnt_, P_, dt_, ctr_,
-                                            world_ > 1 ? seq_base(rank_) : 0ull);
+        k_count<<<n_sm_ * 4, 256, sizeof(CountStage), st_>>>(reinterpret_cast<const int4*>(ids_), reinterpret_cast<const uint4*>(wid_), n4c, wcnt_, P_, dt_, ctr_,
+                                                             world_ > 1 ? seq_base(rank_) : 0ull);
         launches_++;
       }
       CK(cudaEventRecord(ev1_, st_));
@@ -546,28 +504,38 @@ class CudaEngine : public Engine {
       CK(cudaStreamSynchronize(st_));
       CK(cudaGetLastError());
       float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
-      if ((c.err & ERR_DT_FULL) || static_cast<uint64_t>(c.dt_n) * 2 > dt_.cap) {  // enlarge the scratch table, redo (ids untouched)
+      if ((c.err & ERR_DT_FULL) || static_cast<uint64_t>(c.dt_n[0]) * 2 > dt_.cap) {  // enlarge the scratch table, redo (ids untouched)
         RC(alloc_dt(static_cast<uint64_t>(dt_.cap) * 4));
         continue;
       }
-      RC(grow_pt((world_ > 1 ? static_cast<uint64_t>(dt_.cap) / 2 : static_cast<uint64_t>(c.dt_n)) + 4ull * (256 + vocab_hint_) + 1024));  // replicas must size identically
+      RC(grow_pt((world_ > 1 ? static_cast<uint64_t>(dt_.cap) / 2 : static_cast<uint64_t>(c.dt_n[0])) + 4ull * (256 + vocab_hint_) + 1024));  // replicas must size identically
+      CK(cudaEventRecord(ev0_, st_));
+      Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
       if (world_ > 1) {
         DistArgs a_D = next_exchange();
         const int grid = n_sm_ * 2;
-        uint32_t a_reccap = rec_cap_, a_bar = bar_count_;
-        Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
-        uint64_t a_flag = flag_;
+        uint32_t a_reccap = rec_cap_, a_bar = bar_count_, a_par = 0;
+        uint64_t a_flag = flag_, a_pool = pool_cap_;
         bar_count_ += 1u * static_cast<uint32_t>(grid);
-        void* args[] = {&dt_, &pt_, &ctr_, &recs_, &a_reccap, &a_ctrl, &P_, &a_flag, &a_D, &a_bar};
+        void* args[] = {&dt_, &pt_, &ctr_, &a_par, &a_pool, &recs_, &a_reccap, &a_ctrl, &P_, &a_flag, &a_D, &a_bar};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_count_finalize), dim3(grid), dim3(256), args, 0, st_));
       } else {
-        k_finalize_count<<<1, 256, 0, st_>>>(dt_, pt_, ctr_, recs_, rec_cap_, const_cast<Ctrl*>(ctrl_), P_, flag_);
+        k_finalize_count<<<1, 1024, 0, st_>>>(dt_, pt_, ctr_, 0u, pool_cap_, recs_, rec_cap_, a_ctrl, P_, flag_);
       }
       launches_++;
+      if (n_words_) { k_fill_lists<<<n_sm_ * 8, 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_), n4c, P_, pt_, pool_, ctr_); launches_++; }
+      CK(cudaEventRecord(ev1_, st_));
       RC(wait_flag());
       if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", ctrl_->err); return -1; }
+      CK(cudaStreamSynchronize(st_));  // the lists are complete before the first merge reads them (same stream anyway) and before the error check below
+      float ms2 = 0; cudaEventElapsedTime(&ms2, ev0_, ev1_);
+      DevCounters c2;
+      CK(cudaMemcpy(&c2, ctr_, sizeof c2, cudaMemcpyDeviceToHost));
+      if (c2.err) { std::fprintf(stderr, "[ERROR]\t device list fill failed (err=%u)\n", c2.err); return -1; }
       es_.count_launches++; es_.count_device_ms += ms; es_.count_bytes += 4.0 * static_cast<double>(n_slots_) + 12.0 * n_words_;  // 4S + 12N; the kernel reads 8 B per slot + counts
+      es_.fill_device_ms += ms2; es_.fill_bytes += 4.0 * static_cast<double>(n_slots_) + 4.0 * static_cast<double>(ctrl_->pool_top);
       pt_n_ = ctrl_->pt_n;
+      *recs = recs_;  // after the last possible growth of the record buffer (alloc_dt)
       *n = ctrl_->n_recs;
       es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
       return 0;
@@ -576,108 +544,79 @@ class CudaEngine : public Engine {
   }
 
   // --------------------------------------------------------------------------------------------------------- merge
-  int merge(int32_t a, int32_t b, int32_t new_id, uint32_t /*serial*/, uint32_t /*list_len*/, const Rec** recs, size_t* n, uint64_t* occurrences) override {
+  int merge(int32_t a, int32_t b, int32_t new_id, uint32_t serial, uint32_t list_len, const Rec** recs, size_t* n, uint64_t* occurrences) override {
     *recs = recs_; *n = 0; *occurrences = 0;
     const double tm0 = now_ms();
     CK(cudaSetDevice(dev_));  // the caller's thread may have another current device
+    if (a < 0 || b < 0 || new_id < 0 || static_cast<size_t>(std::max(a, b)) >= tok_len_.size() || serial == REC_NO_SERIAL) {
+      std::fprintf(stderr, "[ERROR]\t merge of an unknown token or pair (%d,%d)\n", a, b);
+      return -1;
+    }
+    if (static_cast<size_t>(new_id) >= tok_len_.size()) tok_len_.resize(static_cast<size_t>(new_id) + 1, 1u);
+    const uint32_t lenA = tok_len_[a], lenB = tok_len_[b];
+    tok_len_[new_id] = lenA + lenB;
     // keep the pair table at most half full even if this merge creates every key it can (4 per distinct id)
     const uint64_t worst_new = 4ull * (static_cast<uint64_t>(new_id) + 2);
     if ((pt_n_ + worst_new) * 2 > pt_.cap) RC(grow_pt(pt_n_ + worst_new));
     if (worst_new * 2 > dt_.cap) RC(alloc_dt(next_pow2(worst_new * 2)));
-    // reclaim dead slots once a quarter of the scanned array is dead
-    if (n_slots_ > 4096 && (n_slots_ - n_live_) * 4 > n_slots_) RC(compact());
-    const uint32_t n4 = static_cast<uint32_t>((n_slots_ + 3) / 4);
+    RC(ensure_scratch(list_len));
     const double tl0 = now_ms();
     ++flag_;
+    ++pass_;
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
     const bool profiled = !profile_merges_.empty() && std::find(profile_merges_.begin(), profile_merges_.end(), merge_no_) != profile_merges_.end();
     if (profiled) { cudaStreamSynchronize(st_); cudaProfilerStart(); }
     if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
-    ull* a_dbg = timed ? dbg_ : nullptr;
-    const uint32_t n_tiles = static_cast<uint32_t>((n_slots_ + (1ull << tile_shift_) - 1) >> tile_shift_);
-    int grid = detect_grid(n4);
-    const uint32_t tiles_per_cta = (n_tiles + grid - 1) / grid;
-    const bool indexed = planes_ && static_cast<uint32_t>(a) < id_cap_ && static_cast<uint32_t>(b) < id_cap_;
-    const uint32_t* pa = indexed ? planes_ + static_cast<uint64_t>(a) * plane_words_ : nullptr;
-    const uint32_t* pb = indexed ? planes_ + static_cast<uint64_t>(b) * plane_words_ : nullptr;
+    const int grid = merge_grid(list_len);
+    MergeArgs ma;
+    ma.ids = ids_; ma.wid = wid_; ma.wcnt = wcnt_; ma.pool = pool_; ma.pool_cap = pool_cap_; ma.sc = sc_;
+    ma.A = a; ma.B = b; ma.N = new_id; ma.lenA = lenA; ma.lenB = lenB; ma.serial = serial; ma.par = pass_ & 1u;
+    ma.P = P_; ma.dt = dt_; ma.dt.n = &ctr_->dt_n[pass_ & 1u]; ma.pt = pt_; ma.ctr = ctr_;
+    ma.recs = recs_; ma.rec_cap = rec_cap_; ma.ctrl = const_cast<Ctrl*>(ctrl_); ma.flag_value = flag_;
+    ma.bar_base = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
+    ma.seq_base = world_ > 1 ? seq_base(rank_) : 0ull;
+    ma.dbg = timed ? dbg_ : nullptr;
+    ma.D = dist_;
+    if (world_ > 1) ma.D = next_exchange();
+    bar_count_ += (world_ > 1 ? 3u : 2u) * static_cast<uint32_t>(grid);
     {
-      int4* a_ids = reinterpret_cast<int4*>(ids_[cur_]);
-      uint32_t a_n4 = n4, a_nt = n_tiles, a_tpc = tiles_per_cta, a_ts = tile_shift_, a_W = plane_words_, a_idcap = id_cap_, a_mno = merge_no_, a_reccap = rec_cap_;
-      const uint32_t* a_wid = wid_[cur_]; const ull* a_wcnt = wcnt_; const ull* a_woff = woff_[cur_];
-      int32_t a_A = a, a_B = b, a_N = new_id;
-      Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
-      uint64_t a_flag = flag_;
-      uint32_t a_bar = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
-      DistArgs a_D = dist_;
-      if (world_ > 1) a_D = next_exchange();
-      bar_count_ += (world_ > 1 ? 2u : 1u) * static_cast<uint32_t>(grid);
-      uint32_t a_hot = last_occ_ >= hot_on_occ_ ? 1u : 0u;  // many occurrences last time: CTAs defer and aggregate their emission (kernels_fold.cuh)
-      void* args[] = {&a_ids, &a_n4, &a_nt, &a_tpc, &a_ts, &pa, &pb, &planes_, &a_W, &a_idcap, &a_wid, &a_wcnt, &a_woff, &wlen_, &claimed_, &a_mno, &a_A, &a_B, &a_N,
-                      &P_, &dt_, &pt_, &ctr_, &wl_, &recs_, &a_reccap, &a_ctrl, &a_flag, &a_bar, &a_dbg, &a_D, &a_hot};
-      const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<4, true>) : reinterpret_cast<const void*>(k_merge<4, false>);
-      if (plain_launch_) CK(cudaLaunchKernel(kfn, dim3(grid), dim3(256), args, 0, st_));  // experiment: same grid, no co-residency check by the driver
-      else CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
+      void* args[] = {&ma};
+      const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true>) : reinterpret_cast<const void*>(k_merge<false>);
+      CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
     }
     if (timed) CK(cudaEventRecord(ev1_, st_));
     launches_ += 1;
     launch_ms_ += now_ms() - tl0;
     RC(wait_flag());
-    last_occ_ = ctrl_->occ_local;
     if (profiled) {
       cudaStreamSynchronize(st_); cudaProfilerStop();
-      std::fprintf(stderr, "[PROFILE]\t merge %u pair (%d,%d): slots %llu (algorithmic %llu bytes), candidate tiles %llu of %u (touched %llu bytes), occurrences %llu\n", merge_no_ - 1, a, b,
-                   static_cast<ull>(n_slots_), 4ull * n_slots_, static_cast<ull>(ctrl_->cand_tiles), n_tiles, (4ull << tile_shift_) * ctrl_->cand_tiles, static_cast<ull>(ctrl_->occ));
+      std::fprintf(stderr, "[PROFILE]\t merge %u pair (%d,%d): live slots %llu (algorithmic %llu bytes), list entries %llu, occurrences %llu, keys %llu, grid %d\n", merge_no_ - 1, a, b,
+                   static_cast<ull>(n_live_), 4ull * n_live_, static_cast<ull>(ctrl_->list_len), static_cast<ull>(ctrl_->occ), static_cast<ull>(ctrl_->n_keys), grid);
     }
     if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
     if (timed) {
       float ms = 0;
       CK(cudaEventSynchronize(ev1_));
       cudaEventElapsedTime(&ms, ev0_, ev1_);
-      const double algo = 4.0 * static_cast<double>(n4) * 4.0, touched = 4.0 * static_cast<double>(1u << tile_shift_) * static_cast<double>(ctrl_->cand_tiles);
+      // algorithmic bytes of the scan formulation: 4 B x (live symbols + unique words) -- n_live_ counts both
+      const double algo = 4.0 * static_cast<double>(n_live_), touched = 36.0 * static_cast<double>(ctrl_->list_len) + 88.0 * static_cast<double>(ctrl_->occ_local);
       es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += algo; es_.scan_bytes_touched += touched;
-      const double p1 = (dbg_[1] - dbg_[0]) * 1e-6, p2 = (dbg_[2] - dbg_[1]) * 1e-6, p3 = (dbg_[3] - dbg_[2]) * 1e-6;  // ms: scan+emit+barrier | fold+publish | rewrite
+      const double p1 = (dbg_[1] - dbg_[0]) * 1e-6, p2 = (dbg_[2] - dbg_[1]) * 1e-6, p3 = (dbg_[3] - dbg_[2]) * 1e-6;  // ms: probe+emit+barrier | fold+publish | rewrite (CTA 0)
       es_.scan_phase_ms += p1;
-      if (ctrl_->cand_tiles * 10 >= static_cast<uint64_t>(n_tiles) * 9) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; es_.dense_phase_ms += p1; }  // streams >= 90 % of the array
+      if (ctrl_->list_len >= DENSE_LIST) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; es_.dense_phase_ms += p1; }
       dbg_acc_[0] += p1; dbg_acc_[1] += p2; dbg_acc_[2] += p3; dbg_acc_[3] += ms; dbg_n_++;
       if (dbg_print_ && (dbg_n_ % 500) == 0)
-        std::fprintf(stderr, "[KTIME]\t %llu timed merges: scan+emit+barrier %.1f us, fold+publish %.1f us, rewrite+rearm %.1f us | kernel (events) %.1f us (averages)\n",
+        std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
                      (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
     }
-    cand_tiles_total_ += ctrl_->cand_tiles; tiles_total_ += n_tiles;
+    list_entries_total_ += ctrl_->list_len;
+    *recs = recs_;
     *n = ctrl_->n_recs; *occurrences = ctrl_->occ;
     pt_n_ = ctrl_->pt_n;
     n_live_ -= ctrl_->occ_local;
     es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
     merge_ms_ += now_ms() - tm0;
-    return 0;
-  }
-
-  int compact() {
-    const uint32_t N = n_words_;
-    if (!N) return 0;
-    ull *len1 = nullptr, *sums = nullptr;
-    const uint32_t nb_scan = (N + SCAN_TILE - 1) / SCAN_TILE;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&len1), static_cast<uint64_t>(N) * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8, st_));
-    const int nxt = cur_ ^ 1;
-    k_len1<<<grid_for(N, 256), 256, 0, st_>>>(wlen_, N, len1);
-    k_scan_sums<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums);
-    k_scan_top<<<1, SCAN_THREADS, 0, st_>>>(sums, nb_scan, sums + nb_scan);
-    k_scan_apply<<<nb_scan, SCAN_THREADS, 0, st_>>>(len1, N, sums, woff_[nxt]);
-    ull S1 = 0;
-    CK(cudaMemcpyAsync(&S1, sums + nb_scan, 8, cudaMemcpyDeviceToHost, st_));
-    CK(cudaStreamSynchronize(st_));
-    CK(cudaMemcpyAsync(woff_[nxt] + N, &S1, 8, cudaMemcpyHostToDevice, st_));
-    k_compact<<<grid_for(N, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], woff_[nxt], wlen_, N, ids_[nxt], wid_[nxt]);
-    const uint64_t pad_to = ((S1 + 8 + 1023) / 1024) * 1024;
-    k_fill_i32<<<grid_for(pad_to - S1, 256), 256, 0, st_>>>(ids_[nxt], S1, pad_to < ids_cap_ ? pad_to : ids_cap_, DEAD);
-    launches_ += 6;
-    CK(cudaStreamSynchronize(st_));
-    CK(cudaGetLastError());
-    cudaFreeAsync(len1, st_); cudaFreeAsync(sums, st_);
-    cur_ = nxt; n_slots_ = S1; n_live_ = S1;
-    es_.compactions++;
-    RC(build_planes());
     return 0;
   }
 
@@ -688,7 +627,7 @@ class CudaEngine : public Engine {
     ull* d = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&d), T * 8, st_));
     CK(cudaMemsetAsync(d, 0, T * 8, st_));
-    if (n_words_) { k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_[cur_], woff_[cur_], wlen_, wcnt_, n_words_, P_, d, T); launches_++; }
+    if (n_words_) { k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_, woff_, wcnt_, n_words_, P_, d, T); launches_++; }
     if (world_ > 1) {
       if (T > INBOX_ENTRIES * 3) { cudaFreeAsync(d, st_); std::fprintf(stderr, "[ERROR]\t vocabulary too large for the exchange buffer\n"); return -1; }
       DistArgs a_D = next_exchange();
@@ -718,20 +657,21 @@ class CudaEngine : public Engine {
     if (!loaded_) return -1;
     CK(cudaStreamSynchronize(st_));
     const uint32_t N = n_words_;
-    std::vector<ull> ho(N + 1); std::vector<uint32_t> hl(N ? N : 1); std::vector<int32_t> hi(n_slots_ ? n_slots_ : 1);
+    std::vector<ull> ho(N + 1);
+    std::vector<int32_t> hi(n_slots_ + 2);
     if (N) {
-      CK(cudaMemcpy(ho.data(), woff_[cur_], (static_cast<uint64_t>(N) + 1) * 8, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(hl.data(), wlen_, static_cast<uint64_t>(N) * 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(hi.data(), ids_[cur_], n_slots_ * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(ho.data(), woff_, (static_cast<uint64_t>(N) + 1) * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hi.data(), ids_, (n_slots_ + 2) * 4, cudaMemcpyDeviceToHost));
       if (counts) CK(cudaMemcpy(counts, wcnt_, static_cast<uint64_t>(N) * 8, cudaMemcpyDeviceToHost));
     }
     uint64_t at = 0;
     for (uint32_t wi = 0; wi < N; wi++) {
       if (off) off[wi] = at;
       if (static_cast<uint32_t>(hi[ho[wi]]) != (HDR_BIT | wi)) return -2;  // layout invariant
-      for (uint32_t j = 0; j < hl[wi]; j++) {
-        int32_t code = hi[ho[wi] + 1 + j];
-        if (ids && at < ids_cap) ids[at] = (cfg_.unk_id < 0 && code == UNK_CODE_NEG) ? cfg_.unk_id : code;
+      for (uint64_t q = ho[wi] + 1; q < ho[wi + 1]; q = lay::is_skip(hi[q + 1]) ? q + lay::skip_len(hi[q + 1]) : q + 1) {  // layout.hpp next_start
+        const int32_t code = hi[q];
+        if (code < 0) return -3;  // a token must start here
+        if (ids && at < ids_cap) ids[at] = code_to_id(code, P_);
         at++;
       }
     }
@@ -761,7 +701,7 @@ class CudaEngine : public Engine {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
     out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_; out->merge_ms = merge_ms_;
-    out->cand_tiles = cand_tiles_total_; out->tiles_total = tiles_total_;
+    out->list_entries = list_entries_total_; out->pool_entries = ctrl_ ? ctrl_->pool_top : 0;
   }
   const char* name() override { return name_; }
 
@@ -771,11 +711,13 @@ class CudaEngine : public Engine {
     if (g < 1) g = 1;
     return static_cast<int>(g < maxg ? g : maxg);
   }
-  int detect_grid(uint32_t n4) const {  // persistent grid: SM count x resident CTAs per SM (occupancy query), never more than the work
-    uint64_t warps_needed = (static_cast<uint64_t>(n4) + 127) / 128, ctas = (warps_needed + 7) / 8;
-    uint64_t maxg = static_cast<uint64_t>(n_sm_) * scan_ctas_per_sm_;
-    if (ctas < 1) ctas = 1;
-    return static_cast<int>(ctas < maxg ? ctas : maxg);
+  // grid of a merge launch: one thread per list entry up to the co-resident maximum (cooperative launch); most merges of a
+  // run have a few thousand entries and get a handful of CTAs, which keeps the two grid barriers short
+  static constexpr uint32_t DENSE_LIST = 1u << 16;
+  int merge_grid(uint32_t list_len) const {
+    if (force_grid_ > 0) return force_grid_;
+    const uint64_t ctas = (static_cast<uint64_t>(list_len) + 255) / 256, maxg = static_cast<uint64_t>(n_sm_) * merge_ctas_per_sm_;
+    return static_cast<int>(ctas < 1 ? 1 : (ctas < maxg ? ctas : maxg));
   }
 
   int wait_flag() {
@@ -797,20 +739,23 @@ class CudaEngine : public Engine {
   }
 
   void release_corpus() {
-    for (int i = 0; i < 2; i++) { if (ids_[i]) cudaFreeAsync(ids_[i], st_); ids_[i] = nullptr; if (woff_[i]) cudaFreeAsync(woff_[i], st_); woff_[i] = nullptr; }
+    if (ids_) cudaFreeAsync(ids_, st_); ids_ = nullptr;
+    if (wid_) cudaFreeAsync(wid_, st_); wid_ = nullptr;
+    if (woff_) cudaFreeAsync(woff_, st_); woff_ = nullptr;
     if (wcnt_) cudaFreeAsync(wcnt_, st_); wcnt_ = nullptr;
-    if (wlen_) cudaFreeAsync(wlen_, st_); wlen_ = nullptr;
-    if (wl_) cudaFreeAsync(wl_, st_); wl_ = nullptr;
-    for (int i = 0; i < 2; i++) { if (wid_[i]) cudaFreeAsync(wid_[i], st_); wid_[i] = nullptr; }
-    if (claimed_) cudaFreeAsync(claimed_, st_); claimed_ = nullptr;
-    release_planes(); plane_words_ = 0; id_cap_ = 0; tile_shift_ = 9;
+    if (pool_) cudaFreeAsync(pool_, st_); pool_ = nullptr;
+    pool_cap_ = 0;
     n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
   }
   void release_all() {
     cudaSetDevice(dev_);
     release_corpus();
-    if (dt_.keys) { cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); }
-    if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); }
+    if (dt_.keys) {
+      cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.nocc, st_); cudaFreeAsync(dt_.base, st_);
+      cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_);
+    }
+    if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); cudaFreeAsync(pt_.lists, st_); }
+    if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
     if (recs_) cudaFreeHost(recs_);
     if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
     if (ctr_) cudaFreeAsync(ctr_, st_);
@@ -832,24 +777,21 @@ class CudaEngine : public Engine {
   bool loaded_ = false;
   uint32_t n_words_ = 0;
   uint64_t n_slots_ = 0, n_live_ = 0, ids_cap_ = 0;
-  int32_t* ids_[2] = {nullptr, nullptr};
-  ull* woff_[2] = {nullptr, nullptr};
-  int cur_ = 0;
+  int32_t* ids_ = nullptr;
+  uint32_t* wid_ = nullptr;
+  ull* woff_ = nullptr;
   ull* wcnt_ = nullptr;
-  uint32_t* wlen_ = nullptr;
-  uint32_t* wl_ = nullptr;
-  uint32_t* wid_[2] = {nullptr, nullptr};
-  uint32_t* claimed_ = nullptr;
-  uint32_t merge_no_ = 0, bar_count_ = 0;
+  uint32_t* pool_ = nullptr;
+  uint64_t pool_cap_ = 0;
+  OccScratch sc_{};
+  std::vector<uint32_t> tok_len_ = std::vector<uint32_t>(256, 1u);  // bytes covered by each token id (span length in slots)
+  uint32_t merge_no_ = 0, bar_count_ = 0, pass_ = 0;
   int rank_ = 0, world_ = 1;
   DistArgs dist_{};
   uint8_t* inbox_ = nullptr;
   std::vector<uint64_t> host_counts_;
   std::string rdv_prefix_;
-  uint32_t* planes_ = nullptr;
-  uint64_t planes_bytes_ = 0;
-  uint32_t plane_words_ = 0, id_cap_ = 0, tile_shift_ = 9;
-  uint64_t cand_tiles_total_ = 0, tiles_total_ = 0;
+  uint64_t list_entries_total_ = 0;
   DeltaTable dt_{};
   PairTable pt_{};
   uint64_t pt_n_ = 0;
@@ -864,13 +806,11 @@ class CudaEngine : public Engine {
   double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0;
   int timing_every_ = 0;
   ull* dbg_ = nullptr;
-  bool dbg_print_ = false, plain_launch_ = false;
+  bool dbg_print_ = false;
   std::vector<uint32_t> profile_merges_;
-  uint64_t hot_on_occ_ = 8192;  // SHRED_HOT_ON_OCC: 0 = every launch takes the hot-CTA path (tests), huge = never
-  uint64_t last_occ_ = ~0ull;  // occurrences of the previous merge on this GPU (first merge of a corpus: assume many)
   double dbg_acc_[5] = {0, 0, 0, 0, 0};
   uint64_t dbg_n_ = 0;
-  int scan_ctas_per_sm_ = 4;
+  int merge_ctas_per_sm_ = 4, force_grid_ = 0;
 };
 
 char g_devname[320] = "no CUDA device";

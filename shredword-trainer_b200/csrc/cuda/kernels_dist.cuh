@@ -43,7 +43,10 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
                                                 ull* occ_global) {
   __shared__ bool last_sender;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  const uint32_t n_local = ctr->dt_n < dt.cap ? ctr->dt_n : dt.cap;
+  // Length of this rank's own list.  Folding the peers' entries (below) appends to the same list, so no CTA may start folding
+  // before every CTA has read the length: the fold waits for sent_epoch, which the last CTA to finish sending raises.
+  const uint32_t n_raw = *reinterpret_cast<volatile uint32_t*>(dt.n);
+  const uint32_t n_local = n_raw < dt.cap ? n_raw : dt.cap;
   if (n_local > INBOX_ENTRIES && gtid == 0) atomicOr(&ctr->err, ERR_INBOX_FULL);
   const uint32_t n_send = n_local < INBOX_ENTRIES ? n_local : static_cast<uint32_t>(INBOX_ENTRIES);
   bool sent = false;
@@ -70,11 +73,15 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
   if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out and fenced: raise the flag at the peers
     __threadfence();
     ctr->sent_ctas = 0;
+    *reinterpret_cast<volatile ull*>(&ctr->sent_epoch) = D.xseq;  // every local CTA has read its list length: folding may start
     for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
       *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
   }
   if (threadIdx.x == 0) {  // every CTA waits for the peers' lists to land in MY inbox (local memory)
     const long long t0 = clock64();
+    while (*reinterpret_cast<volatile ull*>(&ctr->sent_epoch) != D.xseq) {
+      if (clock64() - t0 > 8000000000ll) { atomicOr(&ctr->err, ERR_BARRIER); break; }
+    }
     for (int src = 0; src < D.world; src++) if (src != D.rank) {
       volatile ull* f = &reinterpret_cast<InboxHdr*>(inbox_region(D.peer[D.rank], D.world, D.xseq, src))->seq;
       while (*f != D.xseq) {
@@ -100,11 +107,11 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
 }
 
 // count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
-__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, Rec* recs, uint32_t rec_cap, Ctrl* ctrl, Params P,
-                                                             uint64_t flag_value, DistArgs D, uint32_t bar_base) {
+__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, Rec* recs, uint32_t rec_cap,
+                                                             Ctrl* ctrl, Params P, uint64_t flag_value, DistArgs D, uint32_t bar_base) {
   ull occ;
   exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
-  if (blockIdx.x == 0) finalize_block<true>(dt, pt, ctr, recs, rec_cap, ctrl, 0, 0, P, flag_value);
+  if (blockIdx.x == 0) finalize_count_block(dt, pt, ctr, par, pool_cap, recs, rec_cap, ctrl, P, flag_value);
 }
 
 // token frequencies, sharded: sum of the ranks' partial arrays (T x uint64), same inbox protocol

@@ -28,9 +28,14 @@ constexpr uint32_t REC_NO_SERIAL = 0xFFFFFFFFu;
 // Rec.kind carries, above its two kind bits, the length of the occurrence list the device created for the key in this very
 // pass (0 when the key already existed: a pair's occurrences are all created by one pass, afterwards they only disappear).
 constexpr uint32_t REC_KIND_MASK = 3u, REC_LEN_SHIFT = 2u, REC_LEN_MAX = 0x3FFFFFFFu;
-inline uint32_t rec_kind(uint32_t k) { return k & REC_KIND_MASK; }
-inline uint32_t rec_list_len(uint32_t k) { return k >> REC_LEN_SHIFT; }
-inline uint32_t rec_pack(uint32_t kind, uint64_t list_len) { return kind | (static_cast<uint32_t>(list_len < REC_LEN_MAX ? list_len : REC_LEN_MAX) << REC_LEN_SHIFT); }
+#if defined(__CUDACC__)
+#define SHRED_REC_FN __host__ __device__ inline
+#else
+#define SHRED_REC_FN inline
+#endif
+SHRED_REC_FN uint32_t rec_kind(uint32_t k) { return k & REC_KIND_MASK; }
+SHRED_REC_FN uint32_t rec_list_len(uint32_t k) { return k >> REC_LEN_SHIFT; }
+SHRED_REC_FN uint32_t rec_pack(uint32_t kind, uint64_t list_len) { return kind | (static_cast<uint32_t>(list_len < REC_LEN_MAX ? list_len : REC_LEN_MAX) << REC_LEN_SHIFT); }
 
 struct EngineConfig {
   int32_t unk_id;
@@ -47,12 +52,15 @@ struct LoadInfo {
 };
 
 struct EngineStats {
-  uint64_t n_slots, n_symbols_live, pair_entries, compactions;
+  uint64_t n_slots, n_symbols_live, pair_entries;
+  // timed merge launches (every SHRED_TIMING-th): CUDA-event duration, algorithmic bytes of the scan formulation (4 B x (live
+  // symbols + words)) and an estimate of the bytes the launch really touches (list entries, probes, rewrites)
   uint64_t scan_launches; double scan_device_ms; double scan_bytes; double scan_bytes_touched;
-  uint64_t dense_launches; double dense_device_ms; double dense_bytes;  // timed scans that streamed >= 90 % of the array
-  double scan_phase_ms, dense_phase_ms;  // in-kernel %globaltimer: kernel start -> end of the scan phase (all timed / dense timed launches)
-  uint64_t cand_tiles, tiles_total;
+  uint64_t dense_launches; double dense_device_ms; double dense_bytes;  // timed launches whose occurrence list has >= 65536 entries
+  double scan_phase_ms, dense_phase_ms;  // in-kernel %globaltimer: kernel start -> end of phase 1 (all timed / dense timed launches)
+  uint64_t list_entries, pool_entries;   // occurrence-list entries probed by all merges / entries allocated in the pool
   uint64_t count_launches; double count_device_ms; double count_bytes;
+  double fill_device_ms, fill_bytes;     // count pass, second half: fold + initial occurrence lists
   uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;
   uint64_t kernel_launches;
   double h2d_ms, wait_ms, launch_ms, merge_ms;

@@ -390,12 +390,13 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   EngineStats es; std::memset(&es, 0, sizeof es);
   eng_->stats(&es);
   s->n_words = info_.n_words; s->n_symbols_initial = info_.n_symbols; s->n_tokens = info_.n_tokens; s->corpus_bytes = corpus_bytes_;
-  s->n_symbols_live = es.n_symbols_live; s->n_slots = es.n_slots; s->pair_entries = es.pair_entries; s->compactions = es.compactions;
+  s->n_symbols_live = es.n_symbols_live; s->n_slots = es.n_slots; s->pair_entries = es.pair_entries;
+  s->list_entries = es.list_entries; s->pool_entries = es.pool_entries; s->fill_device_ms = es.fill_device_ms; s->fill_bytes = es.fill_bytes;
   s->heap_size = heap_.size(); s->heap_pushes = heap_.pushes; s->heap_pops = heap_.pops;
   s->merges = merges_last_; s->occurrences = occurrences_;
   s->scan_launches = es.scan_launches; s->scan_device_ms = es.scan_device_ms; s->scan_bytes = es.scan_bytes;
   s->scan_bytes_touched = es.scan_bytes_touched; s->dense_launches = es.dense_launches; s->dense_device_ms = es.dense_device_ms; s->dense_bytes = es.dense_bytes;
-  s->cand_tiles = es.cand_tiles; s->tiles_total = es.tiles_total; s->scan_phase_ms = es.scan_phase_ms; s->dense_phase_ms = es.dense_phase_ms;
+  s->scan_phase_ms = es.scan_phase_ms; s->dense_phase_ms = es.dense_phase_ms;
   s->count_launches = es.count_launches; s->count_device_ms = es.count_device_ms; s->count_bytes = es.count_bytes;
   s->ingest_launches = es.ingest_launches; s->ingest_device_ms = es.ingest_device_ms; s->ingest_bytes = es.ingest_bytes;
   s->kernel_launches = es.kernel_launches;

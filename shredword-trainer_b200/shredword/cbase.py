@@ -63,13 +63,13 @@ class Trainer(Structure):  # reference bpe.h:50-60 (+ impl)
 
 class Stats(Structure):  # include/shred_abi.h shred_stats_t
     _fields_ = [(n, c_uint64) for n in ("n_words", "n_symbols_initial", "n_symbols_live", "n_slots", "n_tokens", "corpus_bytes",
-                                        "pair_entries", "heap_size", "heap_pushes", "heap_pops", "merges", "occurrences", "compactions")] + \
+                                        "pair_entries", "heap_size", "heap_pushes", "heap_pops", "merges", "occurrences", "list_entries", "pool_entries")] + \
                [("scan_launches", c_uint64), ("scan_device_ms", c_double), ("scan_bytes", c_double),
-                ("count_launches", c_uint64), ("count_device_ms", c_double), ("count_bytes", c_double),
+                ("count_launches", c_uint64), ("count_device_ms", c_double), ("count_bytes", c_double), ("fill_device_ms", c_double), ("fill_bytes", c_double),
                 ("ingest_launches", c_uint64), ("ingest_device_ms", c_double), ("ingest_bytes", c_double),
                 ("kernel_launches", c_uint64)] + \
                [(n, c_double) for n in ("load_wall_ms", "h2d_ms", "train_wall_ms", "host_heap_ms", "wait_ms", "save_wall_ms", "train_device_ms", "launch_ms", "scan_bytes_touched")] + \
-               [("dense_launches", c_uint64), ("dense_device_ms", c_double), ("dense_bytes", c_double), ("cand_tiles", c_uint64), ("tiles_total", c_uint64), ("scan_phase_ms", c_double), ("dense_phase_ms", c_double)] + \
+               [("dense_launches", c_uint64), ("dense_device_ms", c_double), ("dense_bytes", c_double), ("scan_phase_ms", c_double), ("dense_phase_ms", c_double)] + \
                [("h2d_bytes", c_uint64), ("d2h_bytes", c_uint64), ("tie_root_equal", c_uint64), ("tie_same_as_prev", c_uint64)]
 
     def as_dict(self):

@@ -103,21 +103,42 @@ def test_train_matches_reference_golden(case, T, tmp_path):
     t.destroy()
 
 
-def test_load_from_file_and_compaction(T, tmp_path):
-    """bpe_load_corpus (file path) on a corpus large enough that dead slots get compacted during training"""
+def test_load_from_file_and_list_statistics(T, tmp_path):
+    """bpe_load_corpus (file path); every occurrence a merge rewrites comes out of an occurrence list, so the lists probed
+    cover the occurrences, and the pool holds the initial lists plus the lists of the pairs the merges created"""
     p = generated_corpus(str(tmp_path / "z.txt"), 3_000_000, 11, 14, "zipf")
     o = Oracle(4000, 0, 0.995, 2); o.load_corpus(p); n = o.train()
     t = T(4000, 0, 0.995, 2); t.load_corpus(p)
     assert t.train() == n
     assert t.merges() == o.merges()
     st = t.stats()
-    assert st["compactions"] >= 1
-    assert st["n_symbols_live"] == o.num_symbols
+    assert st["list_entries"] >= st["occurrences"] > 0
+    assert 0 < st["pool_entries"] <= 3 * st["n_symbols_initial"]
+    assert st["n_symbols_live"] == o.num_symbols == st["n_symbols_initial"] - st["occurrences"]
     for i, (ids, cnt) in enumerate(t.words()[:2000]):
         assert ids == o.word_ids(i)
     mo, vo, mg, vg = (str(tmp_path / x) for x in ("mo", "vo", "mg", "vg"))
     o.save(mo, vo); t.save(mg, vg)
     assert open(mo, "rb").read() == open(mg, "rb").read() and open(vo, "rb").read() == open(vg, "rb").read()
+    t.destroy(); o.destroy()
+
+
+def test_table_growth_paths(T):
+    """the delta table (and with it the mapped record buffer) must be able to grow inside count_pairs / merge
+    without the host reading records through a stale pointer: near-random bytes give ~60 k distinct pairs, more than half
+    of the initial 65536-slot delta table; min_pair_freq 1 turns every one of them into a record.  Then train twice."""
+    import random
+    rng = random.Random(5)
+    alphabet = [c for c in range(1, 256) if c not in b"\t\r\n "]
+    data = b" ".join(bytes(rng.choice(alphabet) for _ in range(rng.randint(2, 40))) for _ in range(60000))
+    o = Oracle(700, 0, 0.995, 1); o.load_bytes(data); n = o.train()
+    t = T(700, 0, 0.995, 1); t.load_bytes(data)
+    assert t.train() == n and t.merges() == o.merges()
+    assert t.stats()["pair_entries"] > 40000
+    n2, m2 = o.train(), t.train()   # bpe_train again on the already merged corpus: recount (tokens of every length), lists rebuilt
+    assert m2 == n2 and t.merges() == o.merges()
+    for i, (ids, cnt) in enumerate(t.words()[:500]):
+        assert ids == o.word_ids(i)
     t.destroy(); o.destroy()
 
 
