@@ -80,7 +80,7 @@ class CudaEngine : public Engine {
     void* cp = nullptr;
     CK(cudaHostAlloc(&cp, sizeof(Ctrl), cudaHostAllocMapped));
     std::memset(cp, 0, sizeof(Ctrl));
-    ctrl_ = static_cast<volatile Ctrl*>(cp);
+    ctrl_ = static_cast<Ctrl*>(cp);
     CK(cudaMallocAsync(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters), st_));
     CK(cudaMemset(ctr_, 0, sizeof(DevCounters)));
     CK(cudaEventCreate(&ev0_));
@@ -100,10 +100,10 @@ class CudaEngine : public Engine {
     CK(cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SORT_CAP * sizeof(ull))));
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(CountStage))));
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false, false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
     if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
     if (world_ > 1) {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<true>, 256, 0) == cudaSuccess && nb > 0 && nb < merge_ctas_per_sm_) merge_ctas_per_sm_ = nb;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<true, false>, 256, 0) == cudaSuccess && nb > 0 && nb < merge_ctas_per_sm_) merge_ctas_per_sm_ = nb;
       const char* r = std::getenv("SHRED_RANK");
       rank_ = r ? std::atoi(r) : 0;
       if (world_ > MAX_RANKS || rank_ < 0 || rank_ >= world_) { std::fprintf(stderr, "[ERROR]\t bad SHRED_RANK/SHRED_WORLD (%d/%d, at most %d ranks)\n", rank_, world_, MAX_RANKS); return -1; }
@@ -112,6 +112,7 @@ class CudaEngine : public Engine {
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     if (const char* mg = std::getenv("SHRED_MERGE_GRID")) force_grid_ = std::atoi(mg);  // tests: fixed grid for every merge launch
+    if (const char* sm = std::getenv("SHRED_SINGLE_MAX")) single_max_ = static_cast<uint32_t>(std::strtoul(sm, nullptr, 10));  // longest list handled by the one-CTA variant (0 = never)
     if (const char* pm = std::getenv("SHRED_PROFILE_MERGES")) {  // "0,1,2000": cudaProfilerStart/Stop around these merges (ncu --profile-from-start off)
       for (const char* q = pm; *q;) { char* end = nullptr; const unsigned long v = std::strtoul(q, &end, 10); if (end == q) break; profile_merges_.push_back(static_cast<uint32_t>(v)); q = *end ? end + 1 : end; }
     }
@@ -438,7 +439,8 @@ class CudaEngine : public Engine {
     if (!recs_ || rec_cap_ < dt_.cap) {
       if (recs_) { CK(cudaStreamSynchronize(st_)); cudaFreeHost(recs_); recs_ = nullptr; }
       rec_cap_ = dt_.cap;
-      CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(Rec), cudaHostAllocMapped));
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(WireRec), cudaHostAllocMapped));
+      std::memset(recs_, 0, static_cast<size_t>(rec_cap_) * sizeof(WireRec));  // tag 0 = never written (pass tags start at 1)
     }
     return 0;
   }
@@ -479,7 +481,7 @@ class CudaEngine : public Engine {
   // --------------------------------------------------------------------------------------------------------- count
   int count_pairs(const Rec** recs, size_t* n) override {
     CK(cudaSetDevice(dev_));
-    *recs = recs_; *n = 0;
+    *recs = out_.data(); *n = 0;
     if (!loaded_) return 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
       CK(cudaMemsetAsync(pt_.ent, 0xFF, pt_.cap * sizeof(PairEnt), st_));
@@ -510,33 +512,35 @@ class CudaEngine : public Engine {
       }
       RC(grow_pt((world_ > 1 ? static_cast<uint64_t>(dt_.cap) / 2 : static_cast<uint64_t>(c.dt_n[0])) + 4ull * (256 + vocab_hint_) + 1024));  // replicas must size identically
       CK(cudaEventRecord(ev0_, st_));
-      Ctrl* a_ctrl = const_cast<Ctrl*>(ctrl_);
+      Ctrl* a_ctrl = ctrl_;
+      const uint32_t tag = static_cast<uint32_t>(flag_);
       if (world_ > 1) {
         DistArgs a_D = next_exchange();
         const int grid = n_sm_ * 2;
-        uint32_t a_reccap = rec_cap_, a_bar = bar_count_, a_par = 0;
-        uint64_t a_flag = flag_, a_pool = pool_cap_;
+        uint32_t a_reccap = rec_cap_, a_bar = bar_count_, a_par = 0, a_flag = tag;
+        uint64_t a_pool = pool_cap_;
         bar_count_ += 1u * static_cast<uint32_t>(grid);
         void* args[] = {&dt_, &pt_, &ctr_, &a_par, &a_pool, &recs_, &a_reccap, &a_ctrl, &P_, &a_flag, &a_D, &a_bar};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_count_finalize), dim3(grid), dim3(256), args, 0, st_));
       } else {
-        k_finalize_count<<<1, 1024, 0, st_>>>(dt_, pt_, ctr_, 0u, pool_cap_, recs_, rec_cap_, a_ctrl, P_, flag_);
+        k_finalize_count<<<1, 1024, 0, st_>>>(dt_, pt_, ctr_, 0u, pool_cap_, recs_, rec_cap_, a_ctrl, P_, tag);
       }
       launches_++;
       if (n_words_) { k_fill_lists<<<n_sm_ * 8, 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_), n4c, P_, pt_, pool_, ctr_); launches_++; }
       CK(cudaEventRecord(ev1_, st_));
       RC(wait_flag());
-      if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", ctrl_->err); return -1; }
+      if (cv_.err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", cv_.err); return -1; }
       CK(cudaStreamSynchronize(st_));  // the lists are complete before the first merge reads them (same stream anyway) and before the error check below
       float ms2 = 0; cudaEventElapsedTime(&ms2, ev0_, ev1_);
       DevCounters c2;
       CK(cudaMemcpy(&c2, ctr_, sizeof c2, cudaMemcpyDeviceToHost));
       if (c2.err) { std::fprintf(stderr, "[ERROR]\t device list fill failed (err=%u)\n", c2.err); return -1; }
       es_.count_launches++; es_.count_device_ms += ms; es_.count_bytes += 4.0 * static_cast<double>(n_slots_) + 12.0 * n_words_;  // 4S + 12N; the kernel reads 8 B per slot + counts
-      es_.fill_device_ms += ms2; es_.fill_bytes += 4.0 * static_cast<double>(n_slots_) + 4.0 * static_cast<double>(ctrl_->pool_top);
-      pt_n_ = ctrl_->pt_n;
-      *recs = recs_;  // after the last possible growth of the record buffer (alloc_dt)
-      *n = ctrl_->n_recs;
+      es_.fill_device_ms += ms2; es_.fill_bytes += 4.0 * static_cast<double>(n_slots_) + 4.0 * static_cast<double>(cv_.pool_top);
+      pt_n_ = cv_.pt_n;
+      RC(fetch_records());
+      *recs = out_.data();
+      *n = out_.size();
       es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
       return 0;
     }
@@ -545,7 +549,7 @@ class CudaEngine : public Engine {
 
   // --------------------------------------------------------------------------------------------------------- merge
   int merge(int32_t a, int32_t b, int32_t new_id, uint32_t serial, uint32_t list_len, const Rec** recs, size_t* n, uint64_t* occurrences) override {
-    *recs = recs_; *n = 0; *occurrences = 0;
+    *recs = out_.data(); *n = 0; *occurrences = 0;
     const double tm0 = now_ms();
     CK(cudaSetDevice(dev_));  // the caller's thread may have another current device
     if (a < 0 || b < 0 || new_id < 0 || static_cast<size_t>(std::max(a, b)) >= tok_len_.size() || serial == REC_NO_SERIAL) {
@@ -568,21 +572,25 @@ class CudaEngine : public Engine {
     if (profiled) { cudaStreamSynchronize(st_); cudaProfilerStart(); }
     if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
-    const int grid = merge_grid(list_len);
+    const bool single = world_ == 1 && force_grid_ <= 0 && list_len <= single_max_;
+    const int grid = single ? 1 : merge_grid(list_len);
     MergeArgs ma;
-    ma.ids = ids_; ma.wid = wid_; ma.wcnt = wcnt_; ma.pool = pool_; ma.pool_cap = pool_cap_; ma.sc = sc_;
+    ma.ids = ids_; ma.ids_cap = ids_cap_; ma.wid = wid_; ma.wcnt = wcnt_; ma.pool = pool_; ma.pool_cap = pool_cap_; ma.sc = sc_;
     ma.A = a; ma.B = b; ma.N = new_id; ma.lenA = lenA; ma.lenB = lenB; ma.serial = serial; ma.par = pass_ & 1u;
     ma.P = P_; ma.dt = dt_; ma.dt.n = &ctr_->dt_n[pass_ & 1u]; ma.pt = pt_; ma.ctr = ctr_;
-    ma.recs = recs_; ma.rec_cap = rec_cap_; ma.ctrl = const_cast<Ctrl*>(ctrl_); ma.flag_value = flag_;
+    ma.recs = recs_; ma.rec_cap = rec_cap_; ma.ctrl = ctrl_; ma.tag = static_cast<uint32_t>(flag_);
     ma.bar_base = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
     ma.seq_base = world_ > 1 ? seq_base(rank_) : 0ull;
     ma.dbg = timed ? dbg_ : nullptr;
     ma.D = dist_;
     if (world_ > 1) ma.D = next_exchange();
-    bar_count_ += (world_ > 1 ? 3u : 2u) * static_cast<uint32_t>(grid);
-    {
+    if (single) {
+      k_merge<false, true><<<1, 1024, 0, st_>>>(ma);
+      single_launches_++;
+    } else {
+      bar_count_ += (world_ > 1 ? 3u : 2u) * static_cast<uint32_t>(grid);
       void* args[] = {&ma};
-      const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true>) : reinterpret_cast<const void*>(k_merge<false>);
+      const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true, false>) : reinterpret_cast<const void*>(k_merge<false, false>);
       CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
     }
     if (timed) CK(cudaEventRecord(ev1_, st_));
@@ -592,29 +600,30 @@ class CudaEngine : public Engine {
     if (profiled) {
       cudaStreamSynchronize(st_); cudaProfilerStop();
       std::fprintf(stderr, "[PROFILE]\t merge %u pair (%d,%d): live slots %llu (algorithmic %llu bytes), list entries %llu, occurrences %llu, keys %llu, grid %d\n", merge_no_ - 1, a, b,
-                   static_cast<ull>(n_live_), 4ull * n_live_, static_cast<ull>(ctrl_->list_len), static_cast<ull>(ctrl_->occ), static_cast<ull>(ctrl_->n_keys), grid);
+                   static_cast<ull>(n_live_), 4ull * n_live_, static_cast<ull>(cv_.list_len), static_cast<ull>(cv_.occ), static_cast<ull>(cv_.n_keys), grid);
     }
-    if (ctrl_->err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", ctrl_->err); return -1; }
+    if (cv_.err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", cv_.err); return -1; }
     if (timed) {
       float ms = 0;
       CK(cudaEventSynchronize(ev1_));
       cudaEventElapsedTime(&ms, ev0_, ev1_);
       // algorithmic bytes of the scan formulation: 4 B x (live symbols + unique words) -- n_live_ counts both
-      const double algo = 4.0 * static_cast<double>(n_live_), touched = 36.0 * static_cast<double>(ctrl_->list_len) + 88.0 * static_cast<double>(ctrl_->occ_local);
+      const double algo = 4.0 * static_cast<double>(n_live_), touched = 36.0 * static_cast<double>(cv_.list_len) + 88.0 * static_cast<double>(cv_.occ_local);
       es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += algo; es_.scan_bytes_touched += touched;
       const double p1 = (dbg_[1] - dbg_[0]) * 1e-6, p2 = (dbg_[2] - dbg_[1]) * 1e-6, p3 = (dbg_[3] - dbg_[2]) * 1e-6;  // ms: probe+emit+barrier | fold+publish | rewrite (CTA 0)
-      es_.scan_phase_ms += p1;
-      if (ctrl_->list_len >= DENSE_LIST) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; es_.dense_phase_ms += p1; }
+      es_.scan_phase_ms += p1; es_.fold_phase_ms += p2; es_.rewrite_phase_ms += p3;
+      if (cv_.list_len >= DENSE_LIST) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; es_.dense_phase_ms += p1; }
       dbg_acc_[0] += p1; dbg_acc_[1] += p2; dbg_acc_[2] += p3; dbg_acc_[3] += ms; dbg_n_++;
       if (dbg_print_ && (dbg_n_ % 500) == 0)
         std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
                      (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
     }
-    list_entries_total_ += ctrl_->list_len;
-    *recs = recs_;
-    *n = ctrl_->n_recs; *occurrences = ctrl_->occ;
-    pt_n_ = ctrl_->pt_n;
-    n_live_ -= ctrl_->occ_local;
+    list_entries_total_ += cv_.list_len;
+    RC(fetch_records());
+    *recs = out_.data();
+    *n = out_.size(); *occurrences = cv_.occ;
+    pt_n_ = cv_.pt_n;
+    n_live_ -= cv_.occ_local;
     es_.d2h_bytes += *n * sizeof(Rec) + sizeof(Ctrl);
     merge_ms_ += now_ms() - tm0;
     return 0;
@@ -701,7 +710,7 @@ class CudaEngine : public Engine {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
     out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_; out->merge_ms = merge_ms_;
-    out->list_entries = list_entries_total_; out->pool_entries = ctrl_ ? ctrl_->pool_top : 0;
+    out->list_entries = list_entries_total_; out->pool_entries = cv_.pool_top; out->single_launches = single_launches_;
   }
   const char* name() override { return name_; }
 
@@ -720,21 +729,62 @@ class CudaEngine : public Engine {
     return static_cast<int>(ctas < 1 ? 1 : (ctas < maxg ? ctas : maxg));
   }
 
+  // Spins on the control block until its first 16-byte block carries the current pass tag, then reads the other blocks the same
+  // way (common.cuh: every block is self-validating, the device issues no fence towards the host).
   int wait_flag() {
-    double t0 = now_ms();
+    const double t0 = now_ms();
+    const uint32_t tag = static_cast<uint32_t>(flag_);
+    const volatile ull* w = ctrl_->w;
     uint64_t spins = 0;
-    while (__atomic_load_n(&ctrl_->flag, __ATOMIC_ACQUIRE) != flag_) {
-      if ((++spins & 0x3FFF) == 0) {
-        cudaError_t q = cudaStreamQuery(st_);
-        if (q == cudaSuccess) { if (__atomic_load_n(&ctrl_->flag, __ATOMIC_ACQUIRE) == flag_) break; std::fprintf(stderr, "[ERROR]\t device pass finished without publishing its result\n"); return -1; }
-        if (q != cudaErrorNotReady) { std::fprintf(stderr, "[ERROR]\t CUDA: %s\n", cudaGetErrorString(q)); return -1; }
-        if (now_ms() - t0 > 120000.0) { std::fprintf(stderr, "[ERROR]\t device pass timed out\n"); return -1; }
-      }
+    auto fresh = [&](int blk) { return static_cast<uint32_t>(__atomic_load_n(&w[2 * blk], __ATOMIC_ACQUIRE)) == tag; };
+    for (int blk = 0; blk < 4; blk++) {
+      while (!fresh(blk)) {
+        if ((++spins & 0x3FFF) == 0) {
+          cudaError_t q = cudaStreamQuery(st_);
+          if (q == cudaSuccess) { if (fresh(blk)) break; std::fprintf(stderr, "[ERROR]\t device pass finished without publishing its result\n"); return -1; }
+          if (q != cudaErrorNotReady) { std::fprintf(stderr, "[ERROR]\t CUDA: %s\n", cudaGetErrorString(q)); return -1; }
+          if (now_ms() - t0 > 120000.0) { std::fprintf(stderr, "[ERROR]\t device pass timed out\n"); return -1; }
+        }
 #if defined(__x86_64__)
-      __builtin_ia32_pause();
+        __builtin_ia32_pause();
 #endif
+      }
     }
+    cv_.n_recs = static_cast<uint32_t>(w[0] >> 32); cv_.err = static_cast<uint32_t>(w[1]); cv_.list_len = static_cast<uint32_t>(w[1] >> 32);
+    cv_.occ_local = static_cast<uint32_t>(w[2] >> 32); cv_.occ = w[3];
+    cv_.n_keys = static_cast<uint32_t>(w[4] >> 32); cv_.pt_n = w[5]; cv_.pool_top = w[7];
     wait_ms_ += now_ms() - t0;
+    return 0;
+  }
+  // Decodes the records of the pass just published into out_ (engine.hpp Rec), waiting for any that is still in flight.
+  int fetch_records() {
+    const uint32_t tag = static_cast<uint32_t>(flag_), n = cv_.n_recs;
+    const ull lo = static_cast<ull>(tag & 0xFFFFu), hi = static_cast<ull>(tag >> 16);
+    out_.resize(n);
+    double t0 = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      const volatile ull* w = recs_[i].w;
+      uint64_t spins = 0;
+      ull w1, w2;
+      for (;;) {
+        w1 = __atomic_load_n(&w[1], __ATOMIC_ACQUIRE); w2 = __atomic_load_n(&w[2], __ATOMIC_ACQUIRE);
+        if ((w1 >> 48) == lo && (w2 >> 48) == hi) break;
+        if ((++spins & 0xFFFF) == 0) {
+          if (t0 == 0) t0 = now_ms();
+          if (now_ms() - t0 > 20000.0) { std::fprintf(stderr, "[ERROR]\t record %u of %u never arrived\n", i, n); return -1; }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      Rec& r = out_[i];
+      r.key = w[0];
+      const uint32_t kind = static_cast<uint32_t>(w[3]);
+      r.val = w1 & MASK48;
+      if (rec_kind(kind) == REC_PHANTOM && (r.val >> 47)) r.val |= ~MASK48;  // a phantom's value is a signed net delta
+      r.seq = w2 & MASK48;
+      r.kind = kind; r.serial = static_cast<uint32_t>(w[3] >> 32);
+    }
     return 0;
   }
 
@@ -757,7 +807,7 @@ class CudaEngine : public Engine {
     if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); cudaFreeAsync(pt_.lists, st_); }
     if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
     if (recs_) cudaFreeHost(recs_);
-    if (ctrl_) cudaFreeHost(const_cast<Ctrl*>(ctrl_));
+    if (ctrl_) cudaFreeHost(ctrl_);
     if (ctr_) cudaFreeAsync(ctr_, st_);
     if (st_) cudaStreamSynchronize(st_);
     dist_teardown();
@@ -795,9 +845,13 @@ class CudaEngine : public Engine {
   DeltaTable dt_{};
   PairTable pt_{};
   uint64_t pt_n_ = 0;
-  Rec* recs_ = nullptr;
+  WireRec* recs_ = nullptr;   // mapped pinned host memory the device writes its records into (common.cuh wire format)
   uint32_t rec_cap_ = 0;
-  volatile Ctrl* ctrl_ = nullptr;
+  std::vector<Rec> out_;      // the records of the last pass, decoded for the caller
+  Ctrl* ctrl_ = nullptr;
+  struct CtrlView { uint32_t n_recs = 0, err = 0, list_len = 0, occ_local = 0, n_keys = 0; uint64_t occ = 0, pt_n = 0, pool_top = 0; } cv_;
+  uint32_t single_max_ = 2048;
+  uint64_t single_launches_ = 0;
   DevCounters* ctr_ = nullptr;
   uint64_t flag_ = 0;
   uint64_t vocab_hint_ = 32768;

@@ -107,11 +107,11 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
 }
 
 // count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
-__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, Rec* recs, uint32_t rec_cap,
-                                                             Ctrl* ctrl, Params P, uint64_t flag_value, DistArgs D, uint32_t bar_base) {
+__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, WireRec* recs, uint32_t rec_cap,
+                                                             Ctrl* ctrl, Params P, uint32_t tag, DistArgs D, uint32_t bar_base) {
   ull occ;
   exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
-  if (blockIdx.x == 0) finalize_count_block(dt, pt, ctr, par, pool_cap, recs, rec_cap, ctrl, P, flag_value);
+  if (blockIdx.x == 0) finalize_count_block(dt, pt, ctr, par, pool_cap, recs, rec_cap, ctrl, P, tag);
 }
 
 // token frequencies, sharded: sum of the ranks' partial arrays (T x uint64), same inbox protocol

@@ -11,7 +11,7 @@
 //   * writes the host record (PUSH / DEMOTE / PHANTOM, engine.hpp) when the host has to act on the key.
 template <bool COUNT>
 __device__ __forceinline__ void fold_key(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, uint32_t i, ulonglong2 home, int32_t A, int32_t B, const Params& P,
-                                         uint64_t pool_cap, Rec* recs, uint32_t rec_cap, uint32_t* rec_n, bool* wrote) {
+                                         uint64_t pool_cap, WireRec* recs, uint32_t rec_cap, uint32_t* rec_n, uint32_t tag) {
   const uint64_t key = dt.klist[i];
   const uint32_t ds = dt.list[i];
   const int64_t d = static_cast<int64_t>(dt.delta[ds]);
@@ -48,34 +48,25 @@ __device__ __forceinline__ void fold_key(const DeltaTable& dt, const PairTable& 
   }
   if (emit) {
     const uint32_t idx = atomicAdd(rec_n, 1u);
-    if (idx < rec_cap) recs[idx] = out; else atomicOr(&ctr->err, ERR_REC_FULL);
-    *wrote = true;
+    if (idx < rec_cap) wire_rec(recs + idx, tag, out.key, out.val, out.seq, out.kind, out.serial); else atomicOr(&ctr->err, ERR_REC_FULL);
   }
 }
 
-// Count pass: ONE block folds the aggregated counts, publishes the counters to the host and raises its flag.
-__device__ __forceinline__ void finalize_count_block(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, Rec* recs, uint32_t rec_cap,
-                                                     Ctrl* ctrl, const Params& P, uint64_t flag_value) {
+// Count pass: ONE block folds the aggregated counts and publishes the counters to the host.
+__device__ __forceinline__ void finalize_count_block(const DeltaTable& dt, const PairTable& pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, WireRec* recs, uint32_t rec_cap,
+                                                     Ctrl* ctrl, const Params& P, uint32_t tag) {
   const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(dt.n), dt.cap);
-  bool wrote = false;
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-    fold_key<true>(dt, pt, ctr, i, ld_ent(&pt.ent[mix64(dt.klist[i]) & pt.mask]), 0, 0, P, pool_cap, recs, rec_cap, &ctr->rec_n[par], &wrote);
-  __threadfence_system();  // every thread's records are visible to the host ...
+    fold_key<true>(dt, pt, ctr, i, ld_ent(&pt.ent[mix64(dt.klist[i]) & pt.mask]), 0, 0, P, pool_cap, recs, rec_cap, &ctr->rec_n[par], tag);
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t nr = *reinterpret_cast<volatile uint32_t*>(&ctr->rec_n[par]);
-    ctrl->n_recs = nr < rec_cap ? nr : rec_cap;
-    ctrl->occ = 0; ctrl->occ_local = 0;
-    ctrl->pt_n = *reinterpret_cast<volatile ull*>(&ctr->pt_n);
-    ctrl->pool_top = *reinterpret_cast<volatile ull*>(&ctr->pool_top);
-    ctrl->n_keys = n;
-    ctrl->list_len = 0;
-    ctrl->err = *reinterpret_cast<volatile uint32_t*>(&ctr->err);
-    __threadfence_system();
-    ctrl->flag = flag_value;  // ... before the flag it spins on
+    wire_ctrl(ctrl, tag, nr < rec_cap ? nr : rec_cap, *reinterpret_cast<volatile uint32_t*>(&ctr->err), 0u, 0u, 0ull, n, *reinterpret_cast<volatile ull*>(&ctr->pt_n),
+              *reinterpret_cast<volatile ull*>(&ctr->pool_top));
   }
 }
-__global__ void __launch_bounds__(1024) k_finalize_count(DeltaTable dt, PairTable pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, Rec* recs, uint32_t rec_cap, Ctrl* ctrl,
-                                                         Params P, uint64_t flag_value) {
-  finalize_count_block(dt, pt, ctr, par, pool_cap, recs, rec_cap, ctrl, P, flag_value);
+__global__ void __launch_bounds__(1024) k_finalize_count(DeltaTable dt, PairTable pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, WireRec* recs, uint32_t rec_cap, Ctrl* ctrl,
+                                                         Params P, uint32_t tag) {
+  finalize_count_block(dt, pt, ctr, par, pool_cap, recs, rec_cap, ctrl, P, tag);
 }

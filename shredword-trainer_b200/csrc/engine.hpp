@@ -58,7 +58,9 @@ struct EngineStats {
   uint64_t scan_launches; double scan_device_ms; double scan_bytes; double scan_bytes_touched;
   uint64_t dense_launches; double dense_device_ms; double dense_bytes;  // timed launches whose occurrence list has >= 65536 entries
   double scan_phase_ms, dense_phase_ms;  // in-kernel %globaltimer: kernel start -> end of phase 1 (all timed / dense timed launches)
+  double fold_phase_ms, rewrite_phase_ms;  // same timer: phase 1 end -> published (phase 2) -> CTA 0 done (phase 3), all timed launches
   uint64_t list_entries, pool_entries;   // occurrence-list entries probed by all merges / entries allocated in the pool
+  uint64_t single_launches;              // merges handled by the one-CTA variant of the kernel
   uint64_t count_launches; double count_device_ms; double count_bytes;
   double fill_device_ms, fill_bytes;     // count pass, second half: fold + initial occurrence lists
   uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;

@@ -404,6 +404,7 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->wait_ms = es.wait_ms; s->launch_ms = es.launch_ms; s->save_wall_ms = save_wall_ms_;
   s->h2d_bytes = es.h2d_bytes; s->d2h_bytes = es.d2h_bytes;
   s->tie_root_equal = tie_root_equal_; s->tie_same_as_prev = tie_same_as_prev_;
+  s->fold_phase_ms = es.fold_phase_ms; s->rewrite_phase_ms = es.rewrite_phase_ms; s->single_launches = es.single_launches;
 }
 
 }  // namespace shred
