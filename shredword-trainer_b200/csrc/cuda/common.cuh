@@ -83,13 +83,16 @@ struct DeltaTable {
   uint32_t* n;     // -> DevCounters::dt_n[parity] of the running pass
   uint64_t mask; uint64_t empty; uint32_t cap;
 };
-struct PairEnt { uint64_t key; uint64_t freq; };  // one 16-byte load fetches both
+// One 32-byte sector per pair: key + frequency (one 16-byte load) and, beside them, the serial (a second load of the same sector):
+// a fold touches exactly one DRAM sector per existing pair.
+struct PairEnt { uint64_t key; uint64_t freq; uint32_t serial; uint32_t pad0; uint64_t pad1; };
+struct PoolEnt { uint32_t pos; uint32_t cnt; };  // occurrence-list entry: slot of the pair's first token + its word's count (CNT_SAT: look it up)
+constexpr uint32_t CNT_SAT = 0xFFFFFFFFu;
 // Occurrence list of a pair: positions (slot of the pair's first token) in pool[off, off + len), created by ONE pass -- the
 // count pass, or the merge that created the younger of the two tokens -- and only ever validated lazily afterwards.
 struct ListRef { ull off; uint32_t len; uint32_t fill; };
 struct PairTable {
-  PairEnt* ent;
-  uint32_t* serial;  // dense id per entry = number of entries that existed when it was created (the host indexes by it)
+  PairEnt* ent;      // .serial: dense id per entry = number of entries that existed when it was created (the host indexes by it)
   ListRef* lists;    // indexed by serial (survives rehashing)
   uint64_t mask; uint64_t cap; uint64_t lists_cap;
 };
@@ -120,28 +123,51 @@ __device__ __forceinline__ uint32_t dt_add(const DeltaTable& dt, DevCounters* ct
   return NONE32;
 }
 
-// The four delta-table updates of one occurrence with their memory round trips overlapped (each update alone is a chain
-// load -> CAS -> list reservation of ~0.5 us links): home-slot loads together, claims together, one list reservation
-// for all newly claimed keys.  A key whose home slot holds another key falls back to the probing dt_add.
-// slot_out[j] = the key's slot (NONE32 for an invalid j or a full table).
-__device__ __forceinline__ void dt_add4(const DeltaTable& dt, DevCounters* ctr, const uint64_t (&key)[4], const int64_t (&delta)[4], const uint64_t (&seq)[4],
-                                        uint32_t valid, uint32_t (&slot_out)[4]) {
-  uint64_t slot[4], cur[4], prev[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) { slot[j] = mix64(key[j]) & dt.mask; cur[j] = (valid >> j) & 1u ? dt.keys[slot[j]] : 0ull; slot_out[j] = NONE32; }
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    prev[j] = cur[j];
-    if (((valid >> j) & 1u) && cur[j] == dt.empty)
-      prev[j] = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot[j]]), static_cast<ull>(dt.empty), static_cast<ull>(key[j]));
-  }
+// The four delta-table updates of one occurrence.  Each update alone is a chain home slot -> claim -> list reservation -> add
+// of ~0.5 us links, and a GPU thread issues in order: so the four home slots are resolved together, and then EVERY atomic of the
+// occurrence -- the list reservation for newly claimed keys, the four (delta, seq) reductions, the rank draws of the two keys
+// this merge creates -- is issued before the first result is consumed.  A key whose home slot holds another key takes the
+// probing dt_add afterwards.  cas_first: claim without looking first (one round trip less; for launches with few occurrences,
+// where no key is hot).  want_rank: keys that also draw rank_n[j] consecutive ranks in their future occurrence list (dt.nocc).
+// slot_out[j] / rank_out[j]: the key's slot and rank (NONE32 / 0 when not applicable).
+__device__ __forceinline__ void dt_emit4(const DeltaTable& dt, DevCounters* ctr, const uint64_t (&key)[4], const int64_t (&delta)[4], const uint64_t (&seq)[4],
+                                         uint32_t valid, uint32_t want_rank, const uint32_t (&rank_n)[4], bool cas_first, uint32_t (&slot_out)[4], uint32_t (&rank_out)[4]) {
+  uint64_t slot[4], cur[4];
   uint32_t claimed = 0;
 #pragma unroll
-  for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] == dt.empty) {
-    if (prev[j] == dt.empty) { claimed |= 1u << j; cur[j] = key[j]; } else cur[j] = prev[j];
+  for (int j = 0; j < 4; j++) { slot[j] = mix64(key[j]) & dt.mask; slot_out[j] = NONE32; rank_out[j] = 0; cur[j] = 0ull; }
+  if (cas_first) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) if ((valid >> j) & 1u)
+      cur[j] = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot[j]]), static_cast<ull>(dt.empty), static_cast<ull>(key[j]));
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] == dt.empty) { claimed |= 1u << j; cur[j] = key[j]; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) if ((valid >> j) & 1u) cur[j] = dt.keys[slot[j]];
+    uint64_t prev[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      prev[j] = cur[j];
+      if (((valid >> j) & 1u) && cur[j] == dt.empty)
+        prev[j] = atomicCAS(reinterpret_cast<ull*>(&dt.keys[slot[j]]), static_cast<ull>(dt.empty), static_cast<ull>(key[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] == dt.empty) {
+      if (prev[j] == dt.empty) { claimed |= 1u << j; cur[j] = key[j]; } else cur[j] = prev[j];
+    }
+  }
+  // everything below is issued before anything is consumed
+  uint32_t idx = 0;
+  if (claimed) idx = atomicAdd(dt.n, static_cast<uint32_t>(__popc(claimed)));
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] == key[j]) {
+    atomicAdd(&dt.delta[slot[j]], static_cast<ull>(delta[j]));
+    atomicMin(&dt.seq[slot[j]], static_cast<ull>(seq[j]));
+    slot_out[j] = static_cast<uint32_t>(slot[j]);
+    if ((want_rank >> j) & 1u) rank_out[j] = atomicAdd(&dt.nocc[slot[j]], rank_n[j]);
   }
   if (claimed) {
-    uint32_t idx = atomicAdd(dt.n, static_cast<uint32_t>(__popc(claimed)));
 #pragma unroll
     for (int j = 0; j < 4; j++) if ((claimed >> j) & 1u) {
       if (idx < dt.cap) { dt.list[idx] = static_cast<uint32_t>(slot[j]); dt.klist[idx] = key[j]; }
@@ -149,17 +175,60 @@ __device__ __forceinline__ void dt_add4(const DeltaTable& dt, DevCounters* ctr, 
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; j++) if ((valid >> j) & 1u) {
-    if (cur[j] == key[j]) {
-      atomicAdd(&dt.delta[slot[j]], static_cast<ull>(delta[j]));
-      atomicMin(&dt.seq[slot[j]], static_cast<ull>(seq[j]));
-      slot_out[j] = static_cast<uint32_t>(slot[j]);
-    } else slot_out[j] = dt_add(dt, ctr, key[j], delta[j], seq[j]);
+  for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] != key[j]) {  // home slot taken by another key
+    slot_out[j] = dt_add(dt, ctr, key[j], delta[j], seq[j]);
+    if (((want_rank >> j) & 1u) && slot_out[j] != NONE32) rank_out[j] = atomicAdd(&dt.nocc[slot_out[j]], rank_n[j]);
   }
+}
+
+// ---- warp-level pre-aggregation ---------------------------------------------------------------------------------------------
+// The occurrences a warp handles mostly share their keys (a merge has a few hot neighbours), and same-address atomics serialise:
+// the lanes that hold the same key form a group, one leader applies the group's sum / minimum / size to the table and hands
+// slot and first rank back.  All 32 lanes call these; a lane without a key passes valid = false (it becomes a group of its own).
+struct WarpGroup { uint32_t peers, leader, size, rank; bool lead; };
+__device__ __forceinline__ WarpGroup warp_group(uint64_t key, bool valid, uint64_t never_a_key, uint32_t lane) {
+  WarpGroup g;
+  g.peers = __match_any_sync(0xFFFFFFFFu, valid ? static_cast<ull>(key) : static_cast<ull>(never_a_key | lane));
+  g.leader = __ffs(g.peers) - 1u;
+  g.size = __popc(g.peers);
+  g.rank = __popc(g.peers & ((1u << lane) - 1u));
+  g.lead = valid && lane == g.leader;
+  return g;
+}
+__device__ __forceinline__ uint64_t group_sum_u64(uint32_t peers, uint64_t v) {  // exact for v < 2^61 and up to 32 lanes: three 22-bit limbs (+ the rest)
+  const uint32_t a = __reduce_add_sync(peers, static_cast<uint32_t>(v) & 0x3FFFFFu), b = __reduce_add_sync(peers, static_cast<uint32_t>(v >> 22) & 0x3FFFFFu);
+  const uint32_t c = __reduce_add_sync(peers, static_cast<uint32_t>(v >> 44) & 0x3FFFFu);
+  return static_cast<uint64_t>(a) + (static_cast<uint64_t>(b) << 22) + (static_cast<uint64_t>(c) << 44);
+}
+__device__ __forceinline__ uint64_t group_min_u64(uint32_t peers, uint64_t v) {
+  const uint32_t hi = static_cast<uint32_t>(v >> 32), mh = __reduce_min_sync(peers, hi);
+  const uint32_t ml = __reduce_min_sync(peers, hi == mh ? static_cast<uint32_t>(v) : 0xFFFFFFFFu);
+  return (static_cast<uint64_t>(mh) << 32) | ml;
 }
 
 __device__ __forceinline__ ull gtime() { ull t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ ulonglong2 ld_ent(const PairEnt* e) { return *reinterpret_cast<const ulonglong2*>(e); }
+
+// Finds `key` or claims an empty slot for it WITHOUT assigning the serial (the caller batches the serial counter with its other
+// counters).  Returns the slot; *is_new tells which; *old_freq = its frequency (0 for a new entry).
+__device__ __forceinline__ uint64_t pt_find_or_claim(const PairTable& pt, DevCounters* ctr, uint64_t key, ulonglong2 first, uint64_t* old_freq, bool* is_new) {
+  uint64_t slot = mix64(key) & pt.mask;
+  ulonglong2 e = first;
+  *is_new = false;
+  for (uint64_t probe = 0; probe < pt.cap; ++probe) {
+    if (e.x == key) { *old_freq = e.y; return slot; }
+    if (e.x == PT_EMPTY) {
+      const uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
+      if (prev == PT_EMPTY) { *old_freq = 0; *is_new = true; return slot; }
+      if (prev == key) { *old_freq = pt.ent[slot].freq; return slot; }
+    }
+    slot = (slot + 1) & pt.mask;
+    e = ld_ent(&pt.ent[slot]);
+  }
+  atomicOr(&ctr->err, ERR_PT_FULL);
+  *old_freq = 0;
+  return 0;
+}
 
 // Finds `key` (inserting it if absent) and returns its slot; *old_freq = its frequency (0 for a new entry).
 // `first` is the already-loaded entry at the home slot (lets the caller issue several home loads back to back).
@@ -171,7 +240,7 @@ __device__ __forceinline__ uint64_t pt_find_or_insert(const PairTable& pt, DevCo
     if (e.x == key) { *old_freq = e.y; return slot; }
     if (e.x == PT_EMPTY) {
       const uint64_t prev = atomicCAS(reinterpret_cast<ull*>(&pt.ent[slot].key), static_cast<ull>(PT_EMPTY), static_cast<ull>(key));
-      if (prev == PT_EMPTY) { pt.serial[slot] = static_cast<uint32_t>(atomicAdd(&ctr->pt_n, 1ull)); *old_freq = 0; return slot; }
+      if (prev == PT_EMPTY) { pt.ent[slot].serial = static_cast<uint32_t>(atomicAdd(&ctr->pt_n, 1ull)); *old_freq = 0; return slot; }
       if (prev == key) { *old_freq = pt.ent[slot].freq; return slot; }
     }
     slot = (slot + 1) & pt.mask;

@@ -91,19 +91,20 @@ class CudaEngine : public Engine {
     if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     {  // in-kernel phase timestamps (%globaltimer) of the timed launches
       void* dp = nullptr;
-      CK(cudaHostAlloc(&dp, 8 * sizeof(ull), cudaHostAllocMapped));
+      CK(cudaHostAlloc(&dp, 32 * sizeof(ull), cudaHostAllocMapped));
       dbg_ = static_cast<ull*>(dp);
-      std::memset(dp, 0, 8 * sizeof(ull));
+      std::memset(dp, 0, 32 * sizeof(ull));
       const char* d = std::getenv("SHRED_DEBUG_TIMING");
       dbg_print_ = d && *d && *d != '0';
     }
     CK(cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SORT_CAP * sizeof(ull))));
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(CountStage))));
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false, false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
+    CK(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallStage))));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
     if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
     if (world_ > 1) {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<true, false>, 256, 0) == cudaSuccess && nb > 0 && nb < merge_ctas_per_sm_) merge_ctas_per_sm_ = nb;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<true>, 256, 0) == cudaSuccess && nb > 0 && nb < merge_ctas_per_sm_) merge_ctas_per_sm_ = nb;
       const char* r = std::getenv("SHRED_RANK");
       rank_ = r ? std::atoi(r) : 0;
       if (world_ > MAX_RANKS || rank_ < 0 || rank_ >= world_) { std::fprintf(stderr, "[ERROR]\t bad SHRED_RANK/SHRED_WORLD (%d/%d, at most %d ranks)\n", rank_, world_, MAX_RANKS); return -1; }
@@ -112,7 +113,8 @@ class CudaEngine : public Engine {
     const char* e = std::getenv("SHRED_TIMING");
     timing_every_ = e && *e ? std::atoi(e) : 0;
     if (const char* mg = std::getenv("SHRED_MERGE_GRID")) force_grid_ = std::atoi(mg);  // tests: fixed grid for every merge launch
-    if (const char* sm = std::getenv("SHRED_SINGLE_MAX")) single_max_ = static_cast<uint32_t>(std::strtoul(sm, nullptr, 10));  // longest list handled by the one-CTA variant (0 = never)
+    if (const char* sm = std::getenv("SHRED_SMALL_MAX")) small_max_ = std::min<uint32_t>(SMALL_MAX, static_cast<uint32_t>(std::strtoul(sm, nullptr, 10)));  // longest list k_merge_small takes (0 = never)
+    if (std::getenv("SHRED_SMALL_MAX") && std::strtoul(std::getenv("SHRED_SMALL_MAX"), nullptr, 10) == 0) small_max_ = 0;
     if (const char* pm = std::getenv("SHRED_PROFILE_MERGES")) {  // "0,1,2000": cudaProfilerStart/Stop around these merges (ncu --profile-from-start off)
       for (const char* q = pm; *q;) { char* end = nullptr; const unsigned long v = std::strtoul(q, &end, 10); if (end == q) break; profile_merges_.push_back(static_cast<uint32_t>(v)); q = *end ? end + 1 : end; }
     }
@@ -394,7 +396,7 @@ class CudaEngine : public Engine {
     CK(cudaMemsetAsync(wid_, 0, ids_cap_ * 4, st_));
     // occurrence lists: one entry per adjacent pair of the fresh corpus (< S1) + two per rewritten occurrence (< S1 - words)
     pool_cap_ = S1 + 2 * (S1 - n_local) + 1024;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&pool_), pool_cap_ * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pool_), pool_cap_ * sizeof(PoolEnt), st_));
     CK(cudaMemcpyAsync(d_keep, info->keep, 256, cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(woff_ + n_local, &S1, 8, cudaMemcpyHostToDevice, st_));
     if (n_local) { k_symbolize<<<grid_for(n_local, 256), 256, 0, st_>>>(d_text, wt, order_slot + lo, n_local, woff_, d_keep, P_.unk_code, ids_, wid_); launches_++; es_.ingest_launches++; }
@@ -446,7 +448,6 @@ class CudaEngine : public Engine {
   }
   int alloc_pt(PairTable* pt, uint64_t cap) {
     CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->ent), cap * sizeof(PairEnt), st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->serial), cap * 4, st_));
     pt->cap = cap; pt->mask = cap - 1;
     pt->lists_cap = cap / 2 + 4096;  // the table stays at most half full, serials are dense
     CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->lists), pt->lists_cap * sizeof(ListRef), st_));
@@ -462,7 +463,7 @@ class CudaEngine : public Engine {
     k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
     CK(cudaMemcpyAsync(nt.lists, pt_.lists, pt_.lists_cap * sizeof(ListRef), cudaMemcpyDeviceToDevice, st_));
     CK(cudaStreamSynchronize(st_));
-    cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); cudaFreeAsync(pt_.lists, st_);
+    cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.lists, st_);
     pt_ = nt;
     return 0;
   }
@@ -473,7 +474,7 @@ class CudaEngine : public Engine {
     if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
     if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
     CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.a), cap * sizeof(uint4), st_));
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.b), cap * sizeof(uint2), st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.b), cap * sizeof(uint4), st_));
     sc_.cap = static_cast<uint32_t>(cap);
     return 0;
   }
@@ -526,7 +527,7 @@ class CudaEngine : public Engine {
         k_finalize_count<<<1, 1024, 0, st_>>>(dt_, pt_, ctr_, 0u, pool_cap_, recs_, rec_cap_, a_ctrl, P_, tag);
       }
       launches_++;
-      if (n_words_) { k_fill_lists<<<n_sm_ * 8, 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_), n4c, P_, pt_, pool_, ctr_); launches_++; }
+      if (n_words_) { k_fill_lists<<<n_sm_ * 8, 256, 0, st_>>>(reinterpret_cast<const int4*>(ids_), reinterpret_cast<const uint4*>(wid_), wcnt_, n4c, P_, pt_, pool_, ctr_); launches_++; }
       CK(cudaEventRecord(ev1_, st_));
       RC(wait_flag());
       if (cv_.err) { std::fprintf(stderr, "[ERROR]\t device count pass failed (err=%u)\n", cv_.err); return -1; }
@@ -536,7 +537,7 @@ class CudaEngine : public Engine {
       CK(cudaMemcpy(&c2, ctr_, sizeof c2, cudaMemcpyDeviceToHost));
       if (c2.err) { std::fprintf(stderr, "[ERROR]\t device list fill failed (err=%u)\n", c2.err); return -1; }
       es_.count_launches++; es_.count_device_ms += ms; es_.count_bytes += 4.0 * static_cast<double>(n_slots_) + 12.0 * n_words_;  // 4S + 12N; the kernel reads 8 B per slot + counts
-      es_.fill_device_ms += ms2; es_.fill_bytes += 4.0 * static_cast<double>(n_slots_) + 4.0 * static_cast<double>(cv_.pool_top);
+      es_.fill_device_ms += ms2; es_.fill_bytes += 8.0 * static_cast<double>(n_slots_) + 8.0 * static_cast<double>(cv_.pool_top);
       pt_n_ = cv_.pt_n;
       RC(fetch_records());
       *recs = out_.data();
@@ -564,39 +565,48 @@ class CudaEngine : public Engine {
     if ((pt_n_ + worst_new) * 2 > pt_.cap) RC(grow_pt(pt_n_ + worst_new));
     if (worst_new * 2 > dt_.cap) RC(alloc_dt(next_pow2(worst_new * 2)));
     RC(ensure_scratch(list_len));
-    const double tl0 = now_ms();
-    ++flag_;
-    ++pass_;
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
     const bool profiled = !profile_merges_.empty() && std::find(profile_merges_.begin(), profile_merges_.end(), merge_no_) != profile_merges_.end();
     if (profiled) { cudaStreamSynchronize(st_); cudaProfilerStart(); }
-    if (timed) CK(cudaEventRecord(ev0_, st_));
     ++merge_no_;
-    const bool single = world_ == 1 && force_grid_ <= 0 && list_len <= single_max_;
-    const int grid = single ? 1 : merge_grid(list_len);
-    MergeArgs ma;
-    ma.ids = ids_; ma.ids_cap = ids_cap_; ma.wid = wid_; ma.wcnt = wcnt_; ma.pool = pool_; ma.pool_cap = pool_cap_; ma.sc = sc_;
-    ma.A = a; ma.B = b; ma.N = new_id; ma.lenA = lenA; ma.lenB = lenB; ma.serial = serial; ma.par = pass_ & 1u;
-    ma.P = P_; ma.dt = dt_; ma.dt.n = &ctr_->dt_n[pass_ & 1u]; ma.pt = pt_; ma.ctr = ctr_;
-    ma.recs = recs_; ma.rec_cap = rec_cap_; ma.ctrl = ctrl_; ma.tag = static_cast<uint32_t>(flag_);
-    ma.bar_base = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
-    ma.seq_base = world_ > 1 ? seq_base(rank_) : 0ull;
-    ma.dbg = timed ? dbg_ : nullptr;
-    ma.D = dist_;
-    if (world_ > 1) ma.D = next_exchange();
-    if (single) {
-      k_merge<false, true><<<1, 1024, 0, st_>>>(ma);
-      single_launches_++;
-    } else {
-      bar_count_ += (world_ > 1 ? 3u : 2u) * static_cast<uint32_t>(grid);
-      void* args[] = {&ma};
-      const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true, false>) : reinterpret_cast<const void*>(k_merge<false, false>);
-      CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
+    // one CTA with shared-memory tables for short lists (kernels_merge.cuh k_merge_small); the general kernel otherwise, and
+    // again if the small one had to give up (ERR_RETRY: it has not changed anything then)
+    bool small = world_ == 1 && force_grid_ <= 0 && list_len <= small_max_ && ids_cap_ < (1ull << 30);
+    int grid = 1;
+    for (;;) {
+      const double tl0 = now_ms();
+      ++flag_;
+      if (!small) ++pass_;
+      if (timed) CK(cudaEventRecord(ev0_, st_));
+      grid = small ? 1 : merge_grid(list_len);
+      MergeArgs ma;
+      ma.ids = ids_; ma.ids_cap = ids_cap_; ma.wid = wid_; ma.wcnt = wcnt_; ma.pool = pool_; ma.pool_cap = pool_cap_; ma.sc = sc_;
+      ma.A = a; ma.B = b; ma.N = new_id; ma.lenA = lenA; ma.lenB = lenB; ma.serial = serial; ma.par = pass_ & 1u;
+      ma.P = P_; ma.dt = dt_; ma.dt.n = &ctr_->dt_n[pass_ & 1u]; ma.pt = pt_; ma.ctr = ctr_;
+      ma.recs = recs_; ma.rec_cap = rec_cap_; ma.ctrl = ctrl_; ma.tag = static_cast<uint32_t>(flag_);
+      ma.bar_base = bar_count_;  // barrier counter before this launch; it only grows (wraps mod 2^32)
+      ma.seq_base = world_ > 1 ? seq_base(rank_) : 0ull;
+      ma.dbg = timed ? dbg_ : nullptr;
+      ma.D = dist_;
+      if (small) {
+        const uint32_t nt = std::max<uint32_t>(64u, (list_len + 31u) & ~31u);  // one list entry per thread
+        k_merge_small<<<1, nt, sizeof(SmallStage), st_>>>(ma, small_slots_for(list_len));
+        CK(cudaGetLastError());
+      } else {
+        if (world_ > 1) ma.D = next_exchange();
+        bar_count_ += (world_ > 1 ? 3u : 2u) * static_cast<uint32_t>(grid);
+        void* args[] = {&ma};
+        const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true>) : reinterpret_cast<const void*>(k_merge<false>);
+        CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
+      }
+      if (timed) CK(cudaEventRecord(ev1_, st_));
+      launches_ += 1;
+      launch_ms_ += now_ms() - tl0;
+      RC(wait_flag());
+      if (small && (cv_.err & ERR_RETRY)) { small = false; small_retries_++; continue; }
+      if (small) single_launches_++;
+      break;
     }
-    if (timed) CK(cudaEventRecord(ev1_, st_));
-    launches_ += 1;
-    launch_ms_ += now_ms() - tl0;
-    RC(wait_flag());
     if (profiled) {
       cudaStreamSynchronize(st_); cudaProfilerStop();
       std::fprintf(stderr, "[PROFILE]\t merge %u pair (%d,%d): live slots %llu (algorithmic %llu bytes), list entries %llu, occurrences %llu, keys %llu, grid %d\n", merge_no_ - 1, a, b,
@@ -614,6 +624,7 @@ class CudaEngine : public Engine {
       es_.scan_phase_ms += p1; es_.fold_phase_ms += p2; es_.rewrite_phase_ms += p3;
       if (cv_.list_len >= DENSE_LIST) { es_.dense_launches++; es_.dense_device_ms += ms; es_.dense_bytes += algo; es_.dense_phase_ms += p1; }
       dbg_acc_[0] += p1; dbg_acc_[1] += p2; dbg_acc_[2] += p3; dbg_acc_[3] += ms; dbg_n_++;
+      if (small) { small_acc_[0] += p1; small_acc_[1] += p2; small_acc_[2] += ms; small_n_++; }
       if (dbg_print_ && (dbg_n_ % 500) == 0)
         std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
                      (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
@@ -799,12 +810,18 @@ class CudaEngine : public Engine {
   }
   void release_all() {
     cudaSetDevice(dev_);
+    if (dbg_print_ && dbg_n_) {
+      if (small_n_) std::fprintf(stderr, "[KTIME]\t of which %llu k_merge_small launches: probe+deltas %.1f us, fold+publish %.1f us | kernel (events) %.1f us\n", (unsigned long long)small_n_,
+                                 1e3 * small_acc_[0] / small_n_, 1e3 * small_acc_[1] / small_n_, 1e3 * small_acc_[2] / small_n_);
+      std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
+                   (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
+    }
     release_corpus();
     if (dt_.keys) {
       cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.nocc, st_); cudaFreeAsync(dt_.base, st_);
       cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_);
     }
-    if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.serial, st_); cudaFreeAsync(pt_.lists, st_); }
+    if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.lists, st_); }
     if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
     if (recs_) cudaFreeHost(recs_);
     if (ctrl_) cudaFreeHost(ctrl_);
@@ -831,7 +848,7 @@ class CudaEngine : public Engine {
   uint32_t* wid_ = nullptr;
   ull* woff_ = nullptr;
   ull* wcnt_ = nullptr;
-  uint32_t* pool_ = nullptr;
+  PoolEnt* pool_ = nullptr;
   uint64_t pool_cap_ = 0;
   OccScratch sc_{};
   std::vector<uint32_t> tok_len_ = std::vector<uint32_t>(256, 1u);  // bytes covered by each token id (span length in slots)
@@ -850,8 +867,8 @@ class CudaEngine : public Engine {
   std::vector<Rec> out_;      // the records of the last pass, decoded for the caller
   Ctrl* ctrl_ = nullptr;
   struct CtrlView { uint32_t n_recs = 0, err = 0, list_len = 0, occ_local = 0, n_keys = 0; uint64_t occ = 0, pt_n = 0, pool_top = 0; } cv_;
-  uint32_t single_max_ = 2048;
-  uint64_t single_launches_ = 0;
+  uint32_t small_max_ = SMALL_MAX;
+  uint64_t single_launches_ = 0, small_retries_ = 0;
   DevCounters* ctr_ = nullptr;
   uint64_t flag_ = 0;
   uint64_t vocab_hint_ = 32768;
@@ -863,6 +880,8 @@ class CudaEngine : public Engine {
   bool dbg_print_ = false;
   std::vector<uint32_t> profile_merges_;
   double dbg_acc_[5] = {0, 0, 0, 0, 0};
+  double small_acc_[3] = {0, 0, 0};
+  uint64_t small_n_ = 0;
   uint64_t dbg_n_ = 0;
   int merge_ctas_per_sm_ = 4, force_grid_ = 0;
 };

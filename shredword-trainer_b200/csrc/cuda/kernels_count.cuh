@@ -107,7 +107,8 @@ __device__ __forceinline__ uint64_t pt_lookup(const PairTable& pt, uint64_t key)
 // Second pass of the count: every position whose pair received a list (pairs that reached min_pair_freq) is stored in it.
 // Ranks come from the list's fill cursor; the lanes of a warp that hold the same pair reserve together (one atomic per
 // distinct pair per warp and quarter), so that the few pairs most of a fresh corpus consists of do not serialise on one address.
-__global__ void __launch_bounds__(256) k_fill_lists(const int4* __restrict__ ids4, uint32_t n4, Params P, PairTable pt, uint32_t* __restrict__ pool, DevCounters* ctr) {
+__global__ void __launch_bounds__(256) k_fill_lists(const int4* __restrict__ ids4, const uint4* __restrict__ wid4, const ull* __restrict__ wcnt, uint32_t n4, Params P, PairTable pt,
+                                                    PoolEnt* __restrict__ pool, DevCounters* ctr) {
   const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n4_ceil = (n4 + 31u) & ~31u;
@@ -115,6 +116,8 @@ __global__ void __launch_bounds__(256) k_fill_lists(const int4* __restrict__ ids
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4_ceil; i += stride) {
     const bool in = i < n4;
     const int4 v = in ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+    const uint4 w = in ? __ldg(wid4 + i) : make_uint4(0, 0, 0, 0);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
     const int32_t after = (lane == 31 && i + 1 < n4) ? __ldg(ids + 4 * (static_cast<uint64_t>(i) + 1)) : DEAD;
     int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
     if (lane == 31) nxt = after;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(256) k_fill_lists(const int4* __restrict__ ids
       uint32_t serial = NONE32;
       if (pair_at(ids, 4ull * i + k, s[k], s[k + 1], P, &key)) {
         const uint64_t slot = pt_lookup(pt, key);
-        if (slot != ~0ull) { serial = pt.serial[slot]; if (pt.lists[serial].len == 0) serial = NONE32; }
+        if (slot != ~0ull) { serial = pt.ent[slot].serial; if (pt.lists[serial].len == 0) serial = NONE32; }
       }
       const uint32_t peers = __match_any_sync(0xFFFFFFFFu, serial);
       if (serial != NONE32) {
@@ -134,7 +137,9 @@ __global__ void __launch_bounds__(256) k_fill_lists(const int4* __restrict__ ids
         if (lane == leader) base = atomicAdd(&pt.lists[serial].fill, static_cast<uint32_t>(__popc(peers)));
         base = __shfl_sync(peers, base, leader);
         const ListRef lr = pt.lists[serial];
-        if (base + rank < lr.len) pool[lr.off + base + rank] = static_cast<uint32_t>(4ull * i + k);
+        const ull c = wcnt[ws[k]];
+        PoolEnt e; e.pos = static_cast<uint32_t>(4ull * i + k); e.cnt = c < CNT_SAT ? static_cast<uint32_t>(c) : CNT_SAT;
+        if (base + rank < lr.len) pool[lr.off + base + rank] = e;
         else atomicOr(&ctr->err, ERR_BAD_LIST);
       }
     }

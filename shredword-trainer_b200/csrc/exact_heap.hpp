@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -48,6 +49,7 @@ class ExactHeap {
 
   // heap.cpp:70-79: append, then swap upwards while the parent's freq is strictly smaller.
   void push(PairKey key, uint64_t freq, uint32_t version, uint32_t serial) {
+    if (trace_) { const uint64_t t = freq; std::fwrite(&t, 8, 1, trace_); }
     if (n_ + 1 >= cap_) grow();
     size_t s = ++n_;  // slot of the reference's index n_-1
     while (s > 1) {
@@ -67,6 +69,7 @@ class ExactHeap {
   // heap.cpp:97-111: last entry to the root, then swap with the left child if it is strictly larger, with the right
   // child if it is strictly larger than the better of the two, until neither is.
   HeapEnt pop() {
+    if (trace_) { const uint64_t t = ~0ull; std::fwrite(&t, 8, 1, trace_); }
     const HeapEnt out = top();
     const uint64_t xf = freq_[n_];
     const HeapPayload xp = pay_[n_];
@@ -119,8 +122,12 @@ class ExactHeap {
   }
 
   uint64_t pushes = 0, pops = 0;
+  // development aid: SHRED_HEAP_TRACE=<file> records the operation sequence (push: the frequency, pop: ~0, 8 bytes each), which
+  // is all the heap's structure depends on; tests/bench_heap.cpp replays it to time heap layouts in isolation
+  void set_trace(FILE* f) { trace_ = f; }
 
  private:
+  FILE* trace_ = nullptr;
   // 2 MB aligned, transparent huge pages requested: the arrays are tens of MB and accessed at random
   static void* acquire(size_t bytes) {
     void* p = nullptr;

@@ -57,10 +57,13 @@ TrainerCore::TrainerCore(Trainer* abi, Engine* eng) : abi_(abi), eng_(eng) {
   log_merges_ = e && *e && *e != '0';
   e = std::getenv("SHRED_QUIET");
   quiet_ = e && *e && *e != '0';
+  e = std::getenv("SHRED_HEAP_TRACE");
+  if (e && *e) { trace_file_ = std::fopen(e, "wb"); heap_.set_trace(trace_file_); }
   sync_mirrors();
 }
 
 TrainerCore::~TrainerCore() {
+  if (trace_file_) std::fclose(trace_file_);
   std::free(abi_->merge_ops); abi_->merge_ops = nullptr;
   std::free(abi_->corpus.words); abi_->corpus.words = nullptr;
   std::free(abi_->corpus.word_counts); abi_->corpus.word_counts = nullptr;

@@ -3,6 +3,7 @@
 // Engine for everything that is data parallel.  See trainer_core.cpp for the reference file:line map.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <algorithm>
 #include <string>
 #include <utility>
@@ -67,6 +68,7 @@ class TrainerCore {
   uint64_t tie_root_equal_ = 0, tie_same_as_prev_ = 0, last_merge_freq_ = ~0ull;
   double load_wall_ms_ = 0, train_wall_ms_ = 0, train_device_ms_ = 0, host_heap_ms_ = 0, save_wall_ms_ = 0;
   bool log_merges_ = false, quiet_ = false;
+  FILE* trace_file_ = nullptr;
 };
 
 }  // namespace shred
