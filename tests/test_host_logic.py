@@ -121,3 +121,14 @@ def test_load_from_file_nul_and_empty(hs, tmp_path):
     t = hs.create_trainer(ctypes.byref(_Cfg(300, 0, 0.995, 1)))
     assert hs.bpe_load_corpus(t, os.fsencode(str(tmp_path / "missing.txt"))) == -1
     hs.bpe_trainer_destroy(t)
+
+
+def test_replay_heap_matches_literal_reference(tmp_path):
+    """The product's replay heap (packed words, payload side array, renumbering, adaptive split, wide fallback) against a
+    literal restatement of the reference's heap rules (heap.cpp:53-114) on random operation sequences; tests/heap/bench_heap.cpp"""
+    import subprocess
+    exe = tmp_path / "bench_heap"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(os.path.dirname(os.path.abspath(__file__)), "heap", "bench_heap.cpp")], check=True)
+    for seed in ("1", "2"):
+        r = subprocess.run([str(exe), "check", seed], capture_output=True, text=True)
+        assert r.returncode == 0 and "heap check ok" in r.stdout, r.stdout + r.stderr
