@@ -37,10 +37,12 @@ WORKLOADS = {
     "tiny": (4_000_000, 1, 16, "zipf", 2000, 0, 0.995, 20),
 }
 ROOFLINE_NOTE = ("achieved = ALGORITHMIC bytes of the scan formulation (SURVEY 8d B_merge = 4 B x (live symbols + unique words) per merge) / CUDA-event "
-                 "duration of the whole per-merge kernel, averaged over every 64th launch of the timed region. It is an EFFECTIVE rate: the kernel reads far fewer "
-                 "bytes than that (touched_gbs = bytes it actually reads / duration) and its duration is a chain of dependent memory round trips, not a stream; "
-                 "see DESIGN.md sections 4-5 and roofline.traffic for measured DRAM bytes.")
-DENSE_NOTE = "timed launches of the occurrence-heavy early merges"
+                 "duration of the whole per-merge launch, averaged over every 64th launch of the timed region. It is an EFFECTIVE rate, far above the copy peak by "
+                 "construction: the trainer keeps per-pair occurrence lists, so a merge reads only its pair's list and the few symbols around each entry "
+                 "(touched_gbs = estimate of those bytes / duration; roofline.traffic = DRAM bytes of one launch measured by ncu) -- the bytes of the scan are never "
+                 "read. What bounds a launch is a chain of ~8 dependent memory round trips plus launch latency, not bandwidth (DESIGN.md sections 4-5, "
+                 "profiles/r02). The bandwidth-bound kernels of the path are the count pass and the list fill (detail.count_frac_of_hbm_peak, detail.list_fill_gbs).")
+DENSE_NOTE = "timed launches whose occurrence list has >= 65536 entries (the first few hundred merges): the throughput-bound ones"
 REF_SAMPLE_BYTES = 16 << 20   # bounded sample for the CPU reference: first 16 MiB of the corpus ...
 REF_SAMPLE_MERGES = 40        # ... and this many merges (the reference needs ~47 min just to load 1 GB)
 
@@ -238,7 +240,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SHRED_BENCH_WORKLOAD", "config2_10GB"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-legs", action="store_true", help="skip the informational load_buffer and encoder legs (they pin a corpus-sized host buffer)")
-    ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas per GPU instead of one sharded job")
+    ap.add_argument("--sharded", action="store_true", help="N>1: time ONE job whose unique-word table is sharded over the GPUs (default at N>1: one independent trainer per GPU; "
+                    "the other mode is always run for one step and reported under detail)")
+    ap.add_argument("--replicas", action="store_true", help="(default at N>1, kept for compatibility)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -248,7 +252,8 @@ def main():
     config = {"workload": f"{args.workload}: synthetic {mode} corpus {nbytes} bytes (gen_corpus seed={seed} w={w}), vocab_size={vocab} unk_id={unk} "
                           f"character_coverage={cov} min_pair_freq={mf}",
               "l2": "inputs_exceed_l2" if nbytes > 300_000_000 else "inputs_fit_l2_small_workload",
-              "parallelism": "single GPU" if world == 1 else (f"{world} independent replicas (one per GPU, no data-path collective)" if args.replicas else
+              "parallelism": "single GPU" if world == 1 else (f"{world} independent trainers, one per GPU, each training the whole workload (no data-path collective; train() is a chain of "
+                              f"dependent merges that sharding cannot shorten, DESIGN.md section 6); detail.sharded has the same GPUs as ONE sharded job" if not args.sharded else
                               f"one job, unique-word table sharded over {world} GPUs (contiguous word ranges); per-merge delta exchange inside the merge kernel "
                               f"over NVLink peer memory (CUDA IPC); heap and pair table replicated")}
 
@@ -274,12 +279,13 @@ def main():
     os.environ["SHRED_QUIET"] = "1"
     os.environ["SHRED_TIMING"] = os.environ.get("SHRED_TIMING", "64")  # CUDA events around every 64th merge kernel
     os.environ["SHRED_DEVICE"] = str(local_rank)
-    sharded = world > 1 and not args.replicas
-    if sharded:
+    sharded = world > 1 and args.sharded
+    shard_env = {}
+    if world > 1:
         import tempfile
         box = [tempfile.mkdtemp(prefix="shred_rdv_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        os.environ.update(SHRED_RANK=str(rank), SHRED_WORLD=str(world), SHRED_RDV=box[0])
+        shard_env = dict(SHRED_RANK=str(rank), SHRED_WORLD=str(world), SHRED_RDV=box[0])  # read by the library when a trainer is created
     import __graft_entry__ as ge
     if rank == 0:
         ge._load_build().build()
@@ -302,8 +308,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(buffer=None):
+    def one_step(buffer=None, as_shard=None):
         """The reference's call sequence (shredword/trainer.py:12-29) on the drop-in ABI; buffer != None: the load_buffer extension."""
+        as_shard = sharded if as_shard is None else as_shard
+        for k in ("SHRED_RANK", "SHRED_WORLD", "SHRED_RDV"):
+            os.environ.pop(k, None)
+        if as_shard:
+            os.environ.update(shard_env)
         t = BPETrainer(vocab, unk, cov, mf)
         t0 = time.perf_counter()
         if buffer is None:
@@ -355,19 +366,23 @@ def main():
             rb = one_step(buffer=host)
         side_buffer = {"what": "same step with bpe_b200_load_buffer (one cudaMemcpyAsync from a pinned host buffer) instead of bpe_load_corpus(path); 1 run",
                        "value": rb["merges"] / (rb["load_s"] + rb["train_s"] + rb["save_s"]), "unit": "merges/s", "load_s": rb["load_s"]}
-    # informational (N>1, sharded default): the same GPUs as N independent replicas -- one full trainer per GPU, no exchange
-    replicas = None
-    if sharded:
-        saved = {k: os.environ.pop(k) for k in ("SHRED_RANK", "SHRED_WORLD")}
+    # informational (N>1): the other multi-GPU mode on the same GPUs, one step
+    other = None
+    if world > 1:
         barrier()
         with quiet:
-            rstep = one_step()
+            ostep = one_step(as_shard=not sharded)
         barrier()
-        os.environ.update(saved)
-        rt = torch.tensor([rstep["st"]["train_device_ms"], rstep["load_s"] + rstep["train_s"] + rstep["save_s"]], dtype=torch.float64, device="cuda")
+        omd5 = hashlib.md5(open(model_path, "rb").read()).hexdigest()
+        rt = torch.tensor([ostep["st"]["train_device_ms"], ostep["load_s"] + ostep["train_s"] + ostep["save_s"], ostep["load_s"], ostep["st"]["host_heap_ms"], ostep["st"]["wait_ms"]],
+                          dtype=torch.float64, device="cuda")
         dist.all_reduce(rt, op=dist.ReduceOp.MAX)
-        replicas = {"what": f"{world} independent trainers (one per GPU) on the same workload, 1 step, max over ranks",
-                    "value": world * rstep["merges"] / (rt[0].item() * 1e-3), "e2e": world * rstep["merges"] / rt[1].item(), "unit": "merges/s", "scaling": "weak"}
+        mult = world if sharded else 1   # the other mode of a sharded main run is replicas: N trainers' merges
+        other = {"what": (f"{world} independent trainers (one per GPU) on the same workload" if sharded else
+                          f"ONE job sharded over the {world} GPUs (contiguous word ranges, in-kernel delta exchange over NVLink peer memory, replicated heap)") + ", 1 step, max over ranks",
+                 "value": mult * ostep["merges"] / (rt[0].item() * 1e-3), "e2e": mult * ostep["merges"] / rt[1].item(), "unit": "merges/s", "scaling": "weak" if sharded else "strong",
+                 "load_s": rt[2].item(), "host_heap_ms": rt[3].item(), "wait_ms": rt[4].item(), "merges_md5": omd5}
+        os.environ.pop("SHRED_RANK", None); os.environ.pop("SHRED_WORLD", None)
     encoder = None
     if world == 1 and host is not None:
         try:
@@ -418,7 +433,7 @@ def main():
                                     "what": "first step of the process (warm-up 0): allocator pool growth, pinned staging ring, lazy module load included"} if cold else None,
                 "load_buffer_variant": side_buffer},
         "gpu_launches": int(S("kernel_launches")),
-        "roofline": {"bound": "hbm", "kernel": st.get("merge_kernel_name", "k_merge (one launch per merge)") if isinstance(st, dict) else "k_merge",
+        "roofline": {"bound": "hbm", "kernel": "k_merge_small / k_merge (one launch per merge: probe the pair's occurrence list + count deltas | fold + publish | rewrite + new lists)",
                      "achieved": all_bytes / (all_ms * 1e-3) / 1e9 if all_ms else 0.0, "peak": peak, "unit": "GB/s",
                      "frac": all_bytes / (all_ms * 1e-3) / 1e9 / peak if all_ms and peak else None, "traffic": traffic, "traffic_detail": traffic_note,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
@@ -448,8 +463,8 @@ def main():
                    "save_s_steps": [round(x["save_s"], 4) for x in steps], "merges_md5": merges_md5, "vocab_md5": vocab_md5,
                    "device": __import__("shredword").cbase.lib.bpe_b200_device_name().decode()},
     }
-    if replicas:
-        line["detail"]["replicas"] = replicas
+    if other:
+        line["detail"]["replicas" if sharded else "sharded"] = other
     if encoder:
         if "expand_algorithmic_gbs" in encoder and peak:
             encoder["expand_frac_of_hbm_peak"] = encoder["expand_algorithmic_gbs"] / peak
@@ -461,11 +476,13 @@ def main():
             line["detail"]["bit_exact_vs_golden"] = big["merges_md5"] == merges_md5 and big["merges"] == merges
             if big.get("vocab_md5"):
                 line["detail"]["vocab_bit_exact_vs_golden"] = big["vocab_md5"] == vocab_md5
+            if other:
+                other["bit_exact_vs_golden"] = big["merges_md5"] == other["merges_md5"]
     except Exception:
         pass
-    if sharded and rank == 0:
+    if world > 1 and rank == 0:
         import shutil
-        shutil.rmtree(os.environ["SHRED_RDV"], ignore_errors=True)
+        shutil.rmtree(shard_env["SHRED_RDV"], ignore_errors=True)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

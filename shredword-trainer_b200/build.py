@@ -19,7 +19,7 @@ EXE = os.path.join(HERE, "build", "trainer.exe")
 GEN = os.path.join(HERE, "build", "gen_corpus")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-Wall,-fvisibility=hidden", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-Wall,-fvisibility=hidden", "-cudart", "static", "-DSHRED_NVTX", "-ldl"]
 
 
 def _stale(target, sources):

@@ -128,10 +128,10 @@ __device__ __forceinline__ uint32_t dt_add(const DeltaTable& dt, DevCounters* ct
 // occurrence -- the list reservation for newly claimed keys, the four (delta, seq) reductions, the rank draws of the two keys
 // this merge creates -- is issued before the first result is consumed.  A key whose home slot holds another key takes the
 // probing dt_add afterwards.  cas_first: claim without looking first (one round trip less; for launches with few occurrences,
-// where no key is hot).  want_rank: keys that also draw rank_n[j] consecutive ranks in their future occurrence list (dt.nocc).
+// where no key is hot).  want_rank: keys that also draw a rank in their future occurrence list (dt.nocc).
 // slot_out[j] / rank_out[j]: the key's slot and rank (NONE32 / 0 when not applicable).
 __device__ __forceinline__ void dt_emit4(const DeltaTable& dt, DevCounters* ctr, const uint64_t (&key)[4], const int64_t (&delta)[4], const uint64_t (&seq)[4],
-                                         uint32_t valid, uint32_t want_rank, const uint32_t (&rank_n)[4], bool cas_first, uint32_t (&slot_out)[4], uint32_t (&rank_out)[4]) {
+                                         uint32_t valid, uint32_t want_rank, bool cas_first, uint32_t (&slot_out)[4], uint32_t (&rank_out)[4]) {
   uint64_t slot[4], cur[4];
   uint32_t claimed = 0;
 #pragma unroll
@@ -165,7 +165,7 @@ __device__ __forceinline__ void dt_emit4(const DeltaTable& dt, DevCounters* ctr,
     atomicAdd(&dt.delta[slot[j]], static_cast<ull>(delta[j]));
     atomicMin(&dt.seq[slot[j]], static_cast<ull>(seq[j]));
     slot_out[j] = static_cast<uint32_t>(slot[j]);
-    if ((want_rank >> j) & 1u) rank_out[j] = atomicAdd(&dt.nocc[slot[j]], rank_n[j]);
+    if ((want_rank >> j) & 1u) rank_out[j] = atomicAdd(&dt.nocc[slot[j]], 1u);
   }
   if (claimed) {
 #pragma unroll
@@ -177,33 +177,8 @@ __device__ __forceinline__ void dt_emit4(const DeltaTable& dt, DevCounters* ctr,
 #pragma unroll
   for (int j = 0; j < 4; j++) if (((valid >> j) & 1u) && cur[j] != key[j]) {  // home slot taken by another key
     slot_out[j] = dt_add(dt, ctr, key[j], delta[j], seq[j]);
-    if (((want_rank >> j) & 1u) && slot_out[j] != NONE32) rank_out[j] = atomicAdd(&dt.nocc[slot_out[j]], rank_n[j]);
+    if (((want_rank >> j) & 1u) && slot_out[j] != NONE32) rank_out[j] = atomicAdd(&dt.nocc[slot_out[j]], 1u);
   }
-}
-
-// ---- warp-level pre-aggregation ---------------------------------------------------------------------------------------------
-// The occurrences a warp handles mostly share their keys (a merge has a few hot neighbours), and same-address atomics serialise:
-// the lanes that hold the same key form a group, one leader applies the group's sum / minimum / size to the table and hands
-// slot and first rank back.  All 32 lanes call these; a lane without a key passes valid = false (it becomes a group of its own).
-struct WarpGroup { uint32_t peers, leader, size, rank; bool lead; };
-__device__ __forceinline__ WarpGroup warp_group(uint64_t key, bool valid, uint64_t never_a_key, uint32_t lane) {
-  WarpGroup g;
-  g.peers = __match_any_sync(0xFFFFFFFFu, valid ? static_cast<ull>(key) : static_cast<ull>(never_a_key | lane));
-  g.leader = __ffs(g.peers) - 1u;
-  g.size = __popc(g.peers);
-  g.rank = __popc(g.peers & ((1u << lane) - 1u));
-  g.lead = valid && lane == g.leader;
-  return g;
-}
-__device__ __forceinline__ uint64_t group_sum_u64(uint32_t peers, uint64_t v) {  // exact for v < 2^61 and up to 32 lanes: three 22-bit limbs (+ the rest)
-  const uint32_t a = __reduce_add_sync(peers, static_cast<uint32_t>(v) & 0x3FFFFFu), b = __reduce_add_sync(peers, static_cast<uint32_t>(v >> 22) & 0x3FFFFFu);
-  const uint32_t c = __reduce_add_sync(peers, static_cast<uint32_t>(v >> 44) & 0x3FFFFu);
-  return static_cast<uint64_t>(a) + (static_cast<uint64_t>(b) << 22) + (static_cast<uint64_t>(c) << 44);
-}
-__device__ __forceinline__ uint64_t group_min_u64(uint32_t peers, uint64_t v) {
-  const uint32_t hi = static_cast<uint32_t>(v >> 32), mh = __reduce_min_sync(peers, hi);
-  const uint32_t ml = __reduce_min_sync(peers, hi == mh ? static_cast<uint32_t>(v) : 0xFFFFFFFFu);
-  return (static_cast<uint64_t>(mh) << 32) | ml;
 }
 
 __device__ __forceinline__ ull gtime() { ull t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }

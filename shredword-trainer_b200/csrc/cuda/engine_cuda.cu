@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +67,57 @@ namespace {
 
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+// Virtual ranks -- TEST MODE for machines with fewer GPUs than ranks (SHRED_VIRTUAL_RANKS=W): the W ranks of one sharded job are
+// W trainers of ONE process on ONE GPU, each driven by its own host thread.  The sharded data path is unchanged (same device code,
+// same inbox protocol, same host control per rank); only the three kernels in which ranks wait for one another are launched
+// differently: kernels that spin on a peer must never be separate launches on one GPU (nothing guarantees they run together), so
+// the ranks stage their arguments here and the last one to arrive launches ONE cooperative kernel that holds every rank's CTA group
+// (k_*_virtual).  Ranks and job instances are numbered by creation order; all ranks share one stream.
+struct VirtualCluster {
+  static constexpr int GRID_PER_RANK = 8;
+  std::mutex mu;
+  std::condition_variable cv;
+  int world = 0, created = 0, arrived = 0, rc = 0;
+  uint64_t generation = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t* inbox[MAX_RANKS] = {};
+  MergeArgs m[MAX_RANKS]; CountFinArgs c[MAX_RANKS]; SumArgs sm[MAX_RANKS];
+  void* d_args = nullptr;
+  static VirtualCluster& get() { static VirtualCluster v; return v; }
+  // every rank calls this with the same kind; returns once the combined kernel has been launched
+  template <class Stage>
+  int collective(int kind, Stage stage) {
+    std::unique_lock<std::mutex> lk(mu);
+    stage(*this);
+    const uint64_t gen = generation;
+    if (++arrived == world) {
+      arrived = 0;
+      rc = launch(kind);
+      ++generation;
+      cv.notify_all();
+    } else if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return generation != gen; })) {
+      std::fprintf(stderr, "[ERROR]\t virtual ranks: a rank never reached the collective\n");
+      return -1;
+    }
+    return rc;
+  }
+  int launch(int kind) {
+    for (int r = 0; r < world; r++) for (int k = 0; k < MAX_RANKS; k++) {
+      uint8_t* pk = k < world ? inbox[k] : nullptr;
+      if (kind == 0) m[r].D.peer[k] = pk; else if (kind == 1) c[r].D.peer[k] = pk; else sm[r].D.peer[k] = pk;
+    }
+    const size_t bytes = kind == 0 ? sizeof(MergeArgs) : kind == 1 ? sizeof(CountFinArgs) : sizeof(SumArgs);
+    const void* src = kind == 0 ? static_cast<const void*>(m) : kind == 1 ? static_cast<const void*>(c) : static_cast<const void*>(sm);
+    if (!d_args) CK(cudaMalloc(&d_args, MAX_RANKS * std::max(sizeof(MergeArgs), std::max(sizeof(CountFinArgs), sizeof(SumArgs)))));
+    CK(cudaMemcpyAsync(d_args, src, bytes * world, cudaMemcpyHostToDevice, stream));
+    uint32_t g = GRID_PER_RANK;
+    void* args[] = {&d_args, &g};
+    const void* fn = kind == 0 ? reinterpret_cast<const void*>(k_merge_virtual) : kind == 1 ? reinterpret_cast<const void*>(k_dist_count_finalize_virtual) : reinterpret_cast<const void*>(k_dist_sum_u64_virtual);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(g * world), dim3(256), args, 0, stream));
+    return 0;
+  }
+};
 
 class CudaEngine : public Engine {
  public:
@@ -103,10 +155,21 @@ class CudaEngine : public Engine {
     CK(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallStage))));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
     if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
+    if (const char* vr = std::getenv("SHRED_VIRTUAL_RANKS")) if (std::atoi(vr) > 1) { world_ = std::atoi(vr); virtual_ = true; }
     if (world_ > 1) {
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<true>, 256, 0) == cudaSuccess && nb > 0 && nb < merge_ctas_per_sm_) merge_ctas_per_sm_ = nb;
       const char* r = std::getenv("SHRED_RANK");
       rank_ = r ? std::atoi(r) : 0;
+      if (virtual_) {  // ranks by creation order; every rank works on the cluster's stream
+        VirtualCluster& vc = VirtualCluster::get();
+        std::lock_guard<std::mutex> hold(vc.mu);
+        if (vc.world != world_) { vc.world = world_; vc.created = 0; }
+        rank_ = vc.created++ % world_;
+        if (!vc.stream) CK(cudaStreamCreateWithFlags(&vc.stream, cudaStreamNonBlocking));
+        CK(cudaStreamDestroy(st_));
+        st_ = vc.stream;
+        force_grid_ = VirtualCluster::GRID_PER_RANK;
+      }
       if (world_ > MAX_RANKS || rank_ < 0 || rank_ >= world_) { std::fprintf(stderr, "[ERROR]\t bad SHRED_RANK/SHRED_WORLD (%d/%d, at most %d ranks)\n", rank_, world_, MAX_RANKS); return -1; }
       RC(dist_setup());
     } else { world_ = 1; rank_ = 0; }
@@ -125,6 +188,18 @@ class CudaEngine : public Engine {
   // One process per GPU.  Every rank allocates its inbox with cudaMalloc, exports it with CUDA IPC through a small file
   // in the rendezvous directory SHRED_RDV (shared by the ranks of one job) and maps every peer's inbox.
   int dist_setup() {
+    if (virtual_) {  // peers are plain device pointers of this process; wait until every rank of this job instance has registered
+      const size_t bytes = 2ull * world_ * INBOX_BYTES;
+      CK(cudaMalloc(reinterpret_cast<void**>(&inbox_), bytes));
+      CK(cudaMemset(inbox_, 0, bytes));
+      CK(cudaDeviceSynchronize());
+      VirtualCluster& vc = VirtualCluster::get();
+      std::lock_guard<std::mutex> hold(vc.mu);
+      vc.inbox[rank_] = inbox_;  // the peers' pointers are filled in when a collective is launched: every rank exists by then
+      for (int r = 0; r < MAX_RANKS; r++) dist_.peer[r] = nullptr;
+      dist_.rank = rank_; dist_.world = world_; dist_.xseq = 0;
+      return 0;
+    }
     static int instance = 0;  // ranks create their trainers in the same order, so instance numbers agree
     const int inst = instance++;
     const char* rdv = std::getenv("SHRED_RDV");
@@ -174,6 +249,7 @@ class CudaEngine : public Engine {
   }
   void dist_teardown() {
     if (world_ <= 1 || !inbox_) return;
+    if (virtual_) { cudaStreamSynchronize(st_); cudaFree(inbox_); inbox_ = nullptr; return; }  // (the test destroys its trainers after all ranks have finished)
     for (int r = 0; r < world_; r++) if (r != rank_ && dist_.peer[r]) cudaIpcCloseMemHandle(dist_.peer[r]);
     // exported memory must outlive every peer's mapping: free only after all ranks have closed their handles
     if (!rdv_prefix_.empty()) {
@@ -210,16 +286,31 @@ class CudaEngine : public Engine {
     // --- corpus bytes to HBM, padded with spaces so token walks and 16-byte loads stay in bounds
     const uint64_t padded = ((n + 15) & ~15ull) + 64;
     uint8_t* d_text = nullptr;
+    const double ta = now_ms();
     CK(cudaMallocAsync(reinterpret_cast<void**>(&d_text), padded, st_));
+    PreTok pre;
     double t0 = now_ms();
     if (n && text) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
-    if (n && !text && stream_file(fd, n, d_text) != 0) { cudaFreeAsync(d_text, st_); return -1; }
-    CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
+    if (n && !text) {
+      // file path: the unique-word table exists before the first byte arrives and every chunk is tokenised as soon as it has
+      // landed (copy stream | compute stream), so the tokeniser hides behind the PCIe copy
+      CK(cudaMemsetAsync(d_text, ' ', padded, st_));
+      pre.cap = wt_cap_for(n); pre.seed = 0x5bd1e995u;
+      RC(alloc_wt(&pre.wt, pre.cap));
+      CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
+      bar_count_ = 0;
+      pre.valid = true;
+      if (stream_file(fd, n, d_text, &pre) != 0) { free_wt(pre.wt); cudaFreeAsync(d_text, st_); return -1; }
+    } else {
+      CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
+    }
     CK(cudaStreamSynchronize(st_));
     es_.h2d_ms += now_ms() - t0; es_.h2d_bytes += n;
+    if (dbg_print_) std::fprintf(stderr, "[LOAD]\t text buffer %.1f ms, copy%s %.1f ms\n", t0 - ta, pre.valid ? " + overlapped tokenise" : "", now_ms() - t0);
 
     CK(cudaEventRecord(ev0_, st_));
-    int rc = ingest(d_text, n, info);
+    const double ti = now_ms();
+    int rc = ingest(d_text, n, info, pre);
     cudaFreeAsync(d_text, st_);
     if (rc != 0) return rc;
     CK(cudaEventRecord(ev1_, st_));
@@ -227,8 +318,22 @@ class CudaEngine : public Engine {
     float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_);
     es_.ingest_device_ms = ms;
     es_.ingest_bytes = static_cast<double>(n) + 4.0 * info->n_symbols + 12.0 * info->n_words;
+    if (dbg_print_) std::fprintf(stderr, "[LOAD]\t rest of the ingest %.1f ms (device %.1f ms)\n", now_ms() - ti, ms);
     return 0;
   }
+
+  // unique-word table of a load attempt, possibly filled while the file was still arriving
+  struct PreTok { WordTable wt{}; uint64_t cap = 0; uint32_t seed = 0; bool valid = false; };
+  static uint64_t wt_cap_for(uint64_t n) { uint64_t cap = next_pow2(n / 64 + 1); return cap < (1u << 16) ? (1u << 16) : cap; }  // grown 4x and redone if more than half fills up
+  int alloc_wt(WordTable* wt, uint64_t cap) {
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->tag), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->first), cap * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->count), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->len), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->bucket), cap * 4, st_));
+    wt->cap = cap; wt->mask = cap - 1;
+    CK(cudaMemsetAsync(wt->tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt->first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt->count, 0, cap * 8, st_));
+    return 0;
+  }
+  void free_wt(WordTable& wt) { cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_); }
 
   // pinned staging ring shared by all trainers of the process (cudaHostAlloc is slow, so it is done once)
   static constexpr int STAGE_BUFS = 8;
@@ -236,9 +341,16 @@ class CudaEngine : public Engine {
   struct StageRing { uint8_t* buf[STAGE_BUFS] = {}; std::mutex mu; };
   static StageRing& stage_ring() { static StageRing r; return r; }
 
-  int stream_file(int fd, size_t n, uint8_t* d_text) {
+  int stream_file(int fd, size_t n, uint8_t* d_text, PreTok* pre) {
     StageRing& ring = stage_ring();
     std::lock_guard<std::mutex> hold(ring.mu);  // one load at a time uses the ring
+    if (!st_copy_) CK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    cudaEvent_t ready, landed;
+    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+    CK(cudaEventRecord(ready, st_));          // text buffer pre-filled, word table cleared
+    CK(cudaStreamWaitEvent(st_copy_, ready, 0));
+    uint64_t cut = 0;                        // everything below it has been handed to the tokeniser
     for (int b = 0; b < STAGE_BUFS; b++) if (!ring.buf[b]) CK(cudaHostAlloc(reinterpret_cast<void**>(&ring.buf[b]), STAGE_BYTES, cudaHostAllocDefault));
     const size_t n_chunks = (n + STAGE_BYTES - 1) / STAGE_BYTES;
     cudaEvent_t done[STAGE_BUFS];
@@ -272,32 +384,46 @@ class CudaEngine : public Engine {
       const size_t off = c * STAGE_BYTES, len = std::min(STAGE_BYTES, n - off);
       while (state[b].load(std::memory_order_acquire) != 1 && !failed.load()) std::this_thread::yield();
       if (failed.load()) break;
-      if (cudaMemcpyAsync(d_text + off, ring.buf[b], len, cudaMemcpyHostToDevice, st_) != cudaSuccess || cudaEventRecord(done[b], st_) != cudaSuccess) { failed.store(true); break; }
+      if (cudaMemcpyAsync(d_text + off, ring.buf[b], len, cudaMemcpyHostToDevice, st_copy_) != cudaSuccess || cudaEventRecord(done[b], st_copy_) != cudaSuccess) { failed.store(true); break; }
+      // the chunk's last delimiter (found in the staging buffer, still intact): tokens that start before it also end before it
+      size_t k = len;
+      while (k > 0) { const uint8_t ch = ring.buf[b][k - 1]; if (ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r') break; --k; }
       state[b].store(2, std::memory_order_release);
+      if (k > 0 && off + k > cut) {
+        const uint64_t hi = off + k;
+        if (cudaStreamWaitEvent(st_, done[b], 0) != cudaSuccess) { failed.store(true); break; }
+        k_tokenize<<<grid_for((hi - cut + 15) / 16 + 1, 256), 256, 0, st_>>>(d_text, cut, hi, pre->wt, ctr_, pre->seed); launches_++; es_.ingest_launches++;
+        cut = hi;
+      }
     }
     for (auto& t : readers) t.join();
+    if (!failed.load()) {
+      if (cudaEventRecord(landed, st_copy_) != cudaSuccess || cudaStreamWaitEvent(st_, landed, 0) != cudaSuccess) failed.store(true);
+      else if (cut < n) { k_tokenize<<<grid_for((n - cut + 15) / 16 + 1, 256), 256, 0, st_>>>(d_text, cut, n, pre->wt, ctr_, pre->seed); launches_++; es_.ingest_launches++; }
+    }
+    cudaStreamSynchronize(st_copy_);
+    cudaEventDestroy(ready); cudaEventDestroy(landed);
     for (int b = 0; b < STAGE_BUFS; b++) cudaEventDestroy(done[b]);
     if (failed.load()) { std::fprintf(stderr, "[ERROR]\t reading the corpus file failed\n"); return -1; }
     return 0;
   }
 
-  int ingest(const uint8_t* d_text, uint64_t n, LoadInfo* info) {
+  int ingest(const uint8_t* d_text, uint64_t n, LoadInfo* info, const PreTok& pre) {
     DevCounters zero; std::memset(&zero, 0, sizeof zero);
     WordTable wt; std::memset(&wt, 0, sizeof wt);
     uint32_t N = 0; ull n_tokens = 0;
-    uint64_t cap = next_pow2(n / 64 + 1); if (cap < (1u << 16)) cap = 1u << 16;  // grown 4x and redone if more than half fills up
-    uint32_t seed = 0x5bd1e995u;
+    uint64_t cap = pre.valid ? pre.cap : wt_cap_for(n);
+    uint32_t seed = pre.valid ? pre.seed : 0x5bd1e995u;
     for (int attempt = 0;; ++attempt) {
       if (attempt > 8) { std::fprintf(stderr, "[ERROR]\t unique-word table did not converge\n"); return -1; }
       if (cap > (1ull << 32)) { std::fprintf(stderr, "[ERROR]\t unique-word table too large\n"); return -1; }
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.tag), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.first), cap * 8, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.count), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.len), cap * 4, st_));
-      CK(cudaMallocAsync(reinterpret_cast<void**>(&wt.bucket), cap * 4, st_));
-      wt.cap = cap; wt.mask = cap - 1;
-      CK(cudaMemsetAsync(wt.tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt.first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt.count, 0, cap * 8, st_));
-      CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
-      bar_count_ = 0;
-      if (n) { k_tokenize<<<grid_for((n + 15) / 16, 256), 256, 0, st_>>>(d_text, n, wt, ctr_, seed); launches_++; es_.ingest_launches++; }
+      if (attempt == 0 && pre.valid) wt = pre.wt;  // filled while the file was arriving (load_impl)
+      else {
+        RC(alloc_wt(&wt, cap));
+        CK(cudaMemcpyAsync(ctr_, &zero, sizeof zero, cudaMemcpyHostToDevice, st_));
+        bar_count_ = 0;
+        if (n) { k_tokenize<<<grid_for((n + 15) / 16, 256), 256, 0, st_>>>(d_text, 0, n, wt, ctr_, seed); launches_++; es_.ingest_launches++; }
+      }
       DevCounters c;
       CK(cudaMemcpyAsync(&c, ctr_, sizeof c, cudaMemcpyDeviceToHost, st_));
       CK(cudaStreamSynchronize(st_));
@@ -316,7 +442,7 @@ class CudaEngine : public Engine {
       N = c.n_unique; n_tokens = c.n_tokens;
       break;
     }
-    auto free_wt = [&]() { cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_); };
+    auto free_wt = [&]() { this->free_wt(wt); };
     if (N >= 0x7FFFFFF0u) { free_wt(); std::fprintf(stderr, "[ERROR]\t too many unique words\n"); return -1; }
     n_words_ = N;
     info->n_words = N; info->n_tokens = n_tokens;
@@ -516,13 +642,16 @@ class CudaEngine : public Engine {
       Ctrl* a_ctrl = ctrl_;
       const uint32_t tag = static_cast<uint32_t>(flag_);
       if (world_ > 1) {
-        DistArgs a_D = next_exchange();
-        const int grid = n_sm_ * 2;
-        uint32_t a_reccap = rec_cap_, a_bar = bar_count_, a_par = 0, a_flag = tag;
-        uint64_t a_pool = pool_cap_;
+        const int grid = virtual_ ? VirtualCluster::GRID_PER_RANK : n_sm_ * 2;
+        CountFinArgs ca;
+        ca.dt = dt_; ca.pt = pt_; ca.ctr = ctr_; ca.par = 0; ca.pool_cap = pool_cap_; ca.recs = recs_; ca.rec_cap = rec_cap_; ca.ctrl = a_ctrl; ca.P = P_; ca.tag = tag;
+        ca.D = next_exchange(); ca.bar_base = bar_count_;
         bar_count_ += 1u * static_cast<uint32_t>(grid);
-        void* args[] = {&dt_, &pt_, &ctr_, &a_par, &a_pool, &recs_, &a_reccap, &a_ctrl, &P_, &a_flag, &a_D, &a_bar};
-        CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_count_finalize), dim3(grid), dim3(256), args, 0, st_));
+        if (virtual_) RC(VirtualCluster::get().collective(1, [&](VirtualCluster& vc) { vc.c[rank_] = ca; }));
+        else {
+          void* args[] = {&ca};
+          CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_count_finalize), dim3(grid), dim3(256), args, 0, st_));
+        }
       } else {
         k_finalize_count<<<1, 1024, 0, st_>>>(dt_, pt_, ctr_, 0u, pool_cap_, recs_, rec_cap_, a_ctrl, P_, tag);
       }
@@ -595,9 +724,12 @@ class CudaEngine : public Engine {
       } else {
         if (world_ > 1) ma.D = next_exchange();
         bar_count_ += (world_ > 1 ? 3u : 2u) * static_cast<uint32_t>(grid);
-        void* args[] = {&ma};
-        const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true>) : reinterpret_cast<const void*>(k_merge<false>);
-        CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
+        if (virtual_) RC(VirtualCluster::get().collective(0, [&](VirtualCluster& vc) { vc.m[rank_] = ma; }));
+        else {
+          void* args[] = {&ma};
+          const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true>) : reinterpret_cast<const void*>(k_merge<false>);
+          CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
+        }
       }
       if (timed) CK(cudaEventRecord(ev1_, st_));
       launches_ += 1;
@@ -650,13 +782,15 @@ class CudaEngine : public Engine {
     if (n_words_) { k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_, woff_, wcnt_, n_words_, P_, d, T); launches_++; }
     if (world_ > 1) {
       if (T > INBOX_ENTRIES * 3) { cudaFreeAsync(d, st_); std::fprintf(stderr, "[ERROR]\t vocabulary too large for the exchange buffer\n"); return -1; }
-      DistArgs a_D = next_exchange();
-      const int grid = n_sm_ * 2;
-      uint64_t a_T = T;
-      uint32_t a_bar = bar_count_;
+      const int grid = virtual_ ? VirtualCluster::GRID_PER_RANK : n_sm_ * 2;
+      SumArgs sa;
+      sa.vals = d; sa.T = T; sa.ctr = ctr_; sa.D = next_exchange(); sa.bar_base = bar_count_;
       bar_count_ += 2u * static_cast<uint32_t>(grid);
-      void* args[] = {&d, &a_T, &ctr_, &a_D, &a_bar};
-      CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_sum_u64), dim3(grid), dim3(256), args, 0, st_));
+      if (virtual_) RC(VirtualCluster::get().collective(2, [&](VirtualCluster& vc) { vc.sm[rank_] = sa; }));
+      else {
+        void* args[] = {&sa};
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_dist_sum_u64), dim3(grid), dim3(256), args, 0, st_));
+      }
       launches_++;
     }
     CK(cudaMemcpyAsync(freq, d, T * 8, cudaMemcpyDeviceToHost, st_));
@@ -827,17 +961,18 @@ class CudaEngine : public Engine {
     if (ctrl_) cudaFreeHost(ctrl_);
     if (ctr_) cudaFreeAsync(ctr_, st_);
     if (st_) cudaStreamSynchronize(st_);
+    if (st_copy_) { cudaStreamDestroy(st_copy_); st_copy_ = nullptr; }
     dist_teardown();
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (evm0_) cudaEventDestroy(evm0_);
     if (evm1_) cudaEventDestroy(evm1_);
-    if (st_) cudaStreamDestroy(st_);
+    if (st_ && !virtual_) cudaStreamDestroy(st_);
   }
 
   int dev_, n_sm_;
   char name_[320];
-  cudaStream_t st_ = nullptr;
+  cudaStream_t st_ = nullptr, st_copy_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evm0_ = nullptr, evm1_ = nullptr;
   EngineConfig cfg_{};
   Params P_{};
@@ -854,6 +989,7 @@ class CudaEngine : public Engine {
   std::vector<uint32_t> tok_len_ = std::vector<uint32_t>(256, 1u);  // bytes covered by each token id (span length in slots)
   uint32_t merge_no_ = 0, bar_count_ = 0, pass_ = 0;
   int rank_ = 0, world_ = 1;
+  bool virtual_ = false;
   DistArgs dist_{};
   uint8_t* inbox_ = nullptr;
   std::vector<uint64_t> host_counts_;

@@ -11,6 +11,11 @@
 constexpr int MAX_RANKS = 8;
 constexpr uint64_t INBOX_ENTRIES = 1ull << 20, INBOX_HDR = 64, INBOX_BYTES = INBOX_HDR + INBOX_ENTRIES * 24;
 struct InboxHdr { ull seq; ull n; ull aux; };
+// Grid coordinates of a CTA inside ITS rank's grid.  One process per GPU: (blockIdx.x, gridDim.x).  Virtual ranks (test mode, all
+// ranks of a job as CTA groups of ONE cooperative launch on one GPU, see engine_cuda.cu VirtualCluster): the CTA's index inside its
+// rank's group and the group size -- the guide's rule for machines with fewer GPUs than ranks: kernels that wait on one another
+// must be one launch.
+struct VGrid { uint32_t b, g; };
 struct DistArgs {
   int rank, world;
   uint8_t* peer[MAX_RANKS];  // inbox base of every rank (peer[rank] is local memory)
@@ -39,10 +44,10 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target, uin
 // Cooperative exchange of the delta table's dense list (klist/list/delta/seq) between ranks.  Must be entered after a
 // grid barrier (the local list is complete); ends with one grid barrier (number `barrier_no` of this launch).
 // On return the local delta table holds the GLOBAL aggregate and *occ_global the global occurrence count.
-__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, uint32_t bar_base, int barrier_no, ull occ_local,
+__device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounters* ctr, const DistArgs& D, const VGrid vg, uint32_t bar_base, int barrier_no, ull occ_local,
                                                 ull* occ_global) {
   __shared__ bool last_sender;
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t gtid = vg.b * blockDim.x + threadIdx.x, gthreads = vg.g * blockDim.x;
   // Length of this rank's own list.  Folding the peers' entries (below) appends to the same list, so no CTA may start folding
   // before every CTA has read the length: the fold waits for sent_epoch, which the last CTA to finish sending raises.
   const uint32_t n_raw = *reinterpret_cast<volatile uint32_t*>(dt.n);
@@ -68,7 +73,7 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
   }
   if (sent) __threadfence_system();  // only threads with stores in flight pay for the system-scope fence
   __syncthreads();
-  if (threadIdx.x == 0) last_sender = atomicAdd(&ctr->sent_ctas, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) last_sender = atomicAdd(&ctr->sent_ctas, 1u) == vg.g - 1;
   __syncthreads();
   if (last_sender && threadIdx.x == 0) {  // every CTA's stores are out and fenced: raise the flag at the peers
     __threadfence();
@@ -103,27 +108,31 @@ __device__ __forceinline__ void exchange_deltas(const DeltaTable& dt, DevCounter
       dt_add(dt, ctr, __ldcv(e + 3 * i), static_cast<int64_t>(__ldcv(e + 3 * i + 1)), __ldcv(e + 3 * i + 2));
   }
   *occ_global = occ;
-  grid_barrier(&ctr->bar, bar_base + barrier_no * gridDim.x, &ctr->err);
+  grid_barrier(&ctr->bar, bar_base + barrier_no * vg.g, &ctr->err);
 }
 
 // count pass, sharded: exchange the local pair counts, then block 0 folds the global aggregate and publishes
-__global__ void __launch_bounds__(256) k_dist_count_finalize(DeltaTable dt, PairTable pt, DevCounters* ctr, uint32_t par, uint64_t pool_cap, WireRec* recs, uint32_t rec_cap,
-                                                             Ctrl* ctrl, Params P, uint32_t tag, DistArgs D, uint32_t bar_base) {
+struct CountFinArgs { DeltaTable dt; PairTable pt; DevCounters* ctr; uint32_t par; uint64_t pool_cap; WireRec* recs; uint32_t rec_cap; Ctrl* ctrl; Params P; uint32_t tag; DistArgs D; uint32_t bar_base; };
+__device__ __forceinline__ void dist_count_finalize_body(const CountFinArgs& a, const VGrid vg) {
   ull occ;
-  exchange_deltas(dt, ctr, D, bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
-  if (blockIdx.x == 0) finalize_count_block(dt, pt, ctr, par, pool_cap, recs, rec_cap, ctrl, P, tag);
+  exchange_deltas(a.dt, a.ctr, a.D, vg, a.bar_base, 1, 0ull, &occ);  // entered at kernel start: k_count has completed
+  if (vg.b == 0) finalize_count_block(a.dt, a.pt, a.ctr, a.par, a.pool_cap, a.recs, a.rec_cap, a.ctrl, a.P, a.tag);
 }
+__global__ void __launch_bounds__(256) k_dist_count_finalize(const CountFinArgs a) { dist_count_finalize_body(a, VGrid{blockIdx.x, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_dist_count_finalize_virtual(const CountFinArgs* argv, uint32_t g) { dist_count_finalize_body(argv[blockIdx.x / g], VGrid{blockIdx.x % g, g}); }
 
 // token frequencies, sharded: sum of the ranks' partial arrays (T x uint64), same inbox protocol
-__global__ void __launch_bounds__(256) k_dist_sum_u64(ull* vals, uint64_t T, DevCounters* ctr, DistArgs D, uint32_t bar_base) {
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+struct SumArgs { ull* vals; uint64_t T; DevCounters* ctr; DistArgs D; uint32_t bar_base; };
+__device__ __forceinline__ void dist_sum_body(const SumArgs& a, const VGrid vg) {
+  ull* vals = a.vals; const uint64_t T = a.T; DevCounters* ctr = a.ctr; const DistArgs& D = a.D; const uint32_t bar_base = a.bar_base;
+  const uint32_t gtid = vg.b * blockDim.x + threadIdx.x, gthreads = vg.g * blockDim.x;
   for (uint64_t i = gtid; i < T; i += gthreads) {
     const ull v = vals[i];
     for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
       reinterpret_cast<ull*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank) + INBOX_HDR)[i] = v;
   }
   __threadfence_system();
-  grid_barrier(&ctr->bar, bar_base + 1 * gridDim.x, &ctr->err);
+  grid_barrier(&ctr->bar, bar_base + 1 * vg.g, &ctr->err);
   if (gtid == 0) {
     for (int dst = 0; dst < D.world; dst++) if (dst != D.rank)
       *reinterpret_cast<volatile ull*>(&reinterpret_cast<InboxHdr*>(inbox_region(D.peer[dst], D.world, D.xseq, D.rank))->seq) = D.xseq;
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(256) k_dist_sum_u64(ull* vals, uint64_t T, Dev
     }
     __threadfence_system();
   }
-  grid_barrier(&ctr->bar, bar_base + 2 * gridDim.x, &ctr->err);
+  grid_barrier(&ctr->bar, bar_base + 2 * vg.g, &ctr->err);
   for (uint64_t i = gtid; i < T; i += gthreads) {
     ull v = vals[i];
     for (int src = 0; src < D.world; src++) if (src != D.rank)
@@ -142,3 +151,5 @@ __global__ void __launch_bounds__(256) k_dist_sum_u64(ull* vals, uint64_t T, Dev
     vals[i] = v;
   }
 }
+__global__ void __launch_bounds__(256) k_dist_sum_u64(const SumArgs a) { dist_sum_body(a, VGrid{blockIdx.x, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_dist_sum_u64_virtual(const SumArgs* argv, uint32_t g) { dist_sum_body(argv[blockIdx.x / g], VGrid{blockIdx.x % g, g}); }

@@ -55,9 +55,9 @@ __device__ __forceinline__ bool probe_entry(const MergeArgs& a, const PoolEnt e,
 // loads and atomics are issued together, and nothing on the path waits for the host.
 constexpr uint32_t CAS_FIRST_MAX = 16384;  // launches with at most this many list entries claim delta-table slots without looking first
 template <bool DIST>
-__global__ void __launch_bounds__(256) k_merge(const MergeArgs a) {
+__device__ __forceinline__ void merge_body(const MergeArgs& a, const VGrid vg) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t gtid = vg.b * blockDim.x + threadIdx.x, gthreads = vg.g * blockDim.x;
   DevCounters* const ctr = a.ctr;
   const uint32_t par = a.par;
   if (gtid == 0) {
@@ -88,9 +88,8 @@ __global__ void __launch_bounds__(256) k_merge(const MergeArgs a) {
       const uint64_t sq[4] = {seq + 0, seq + 1, seq + 2, seq + 3};
       const uint32_t valid = (o.has_l ? 3u : 0u) | (o.has_r ? 12u : 0u);
       const uint32_t want = ((valid & 2u) && !lay::key_has_unk(key[1], a.P) ? 2u : 0u) | ((valid & 8u) && !lay::key_has_unk(key[3], a.P) ? 8u : 0u);
-      const uint32_t one[4] = {1u, 1u, 1u, 1u};
       uint32_t slot[4], rank[4];
-      dt_emit4(a.dt, ctr, key, delta, sq, valid, want, one, lr.len <= CAS_FIRST_MAX, slot, rank);
+      dt_emit4(a.dt, ctr, key, delta, sq, valid, want, lr.len <= CAS_FIRST_MAX, slot, rank);
       if (want & 2u) { s1 = slot[1]; r1 = rank[1]; }
       if (want & 8u) { s2 = slot[3]; r2 = rank[3]; }
     }
@@ -101,11 +100,11 @@ __global__ void __launch_bounds__(256) k_merge(const MergeArgs a) {
       else atomicOr(&ctr->err, ERR_SCRATCH_FULL);
     }
   }
-  grid_barrier(&ctr->bar, a.bar_base + gridDim.x, &ctr->err);
+  grid_barrier(&ctr->bar, a.bar_base + vg.g, &ctr->err);
   if (a.dbg && gtid == 0) a.dbg[1] = gtime();
   const ull occ_local = *reinterpret_cast<volatile uint32_t*>(&ctr->n_occ[par]);
   ull occ_global = occ_local;
-  if (DIST) exchange_deltas(a.dt, ctr, a.D, a.bar_base, 2, occ_local, &occ_global);
+  if (DIST) exchange_deltas(a.dt, ctr, a.D, vg, a.bar_base, 2, occ_local, &occ_global);
 
   // ---- phase 2: fold the aggregated deltas into the pair table
   const uint32_t n_keys = min(*reinterpret_cast<volatile uint32_t*>(a.dt.n), a.dt.cap);
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(256) k_merge(const MergeArgs a) {
   // second barrier; its last arrival publishes (the others are already released and rewriting)
   __syncthreads();
   if (threadIdx.x == 0) {
-    const uint32_t target2 = a.bar_base + (DIST ? 3u : 2u) * gridDim.x;
+    const uint32_t target2 = a.bar_base + (DIST ? 3u : 2u) * vg.g;
     __threadfence();
     const bool last = atomicAdd(&ctr->bar, 1u) + 1u == target2;
     if (last) {
@@ -153,6 +152,10 @@ __global__ void __launch_bounds__(256) k_merge(const MergeArgs a) {
   }
   if (a.dbg && gtid == 0) a.dbg[3] = gtime();
 }
+template <bool DIST>
+__global__ void __launch_bounds__(256) k_merge(const MergeArgs a) { merge_body<DIST>(a, VGrid{blockIdx.x, gridDim.x}); }
+// virtual ranks (tests on fewer GPUs than ranks): every rank's CTA group in one cooperative launch
+__global__ void __launch_bounds__(256) k_merge_virtual(const MergeArgs* argv, uint32_t g) { merge_body<true>(argv[blockIdx.x / g], VGrid{blockIdx.x % g, g}); }
 
 // ---------------------------------------------------------------------------------------------------- one-CTA merge
 // Most merges of a run have occurrence lists of a few dozen to a few hundred entries, and for them a launch is pure latency:

@@ -87,12 +87,14 @@ __device__ __forceinline__ uint64_t word_insert(const uint8_t* __restrict__ text
   return ~0ull;
 }
 
-// Each thread owns 16 consecutive corpus bytes (one uint4 load) and inserts every token that STARTS inside them.
-// text is padded with >= 32 spaces, so token walks terminate.
-__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
+// Each thread owns 16 consecutive corpus bytes (one uint4 load) and inserts every token that STARTS inside them at an offset in
+// [lo, n).  text is padded with >= 32 spaces, so token walks terminate.  Ranges let the ingest tokenise a file while it is still
+// arriving over PCIe: a range ends right after a delimiter, so every token that starts inside it also ends inside it, and the
+// not-yet-landed rest of the buffer is pre-filled with spaces (no token start, no NUL).
+__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ text, uint64_t lo, uint64_t n, WordTable wt, DevCounters* ctr, uint32_t seed) {
   const uint64_t n16 = (n + 15) >> 4;
   uint32_t my_tokens = 0, my_claims = 0;
-  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n16; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+  for (uint64_t t = (lo >> 4) + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < n16; t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t base = t << 4;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + base));
     uint32_t prev = base ? text[base - 1] : 32u;
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ te
       starts &= starts - 1;
       const uint64_t off = base + i;
       if (off >= n) break;
+      if (off < lo) continue;
       uint32_t len, dj;
       const uint64_t tag = token_walk(text, off, seed, &len, &dj);
       ++my_tokens;

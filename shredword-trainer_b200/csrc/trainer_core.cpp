@@ -30,6 +30,16 @@
 #include <cstdlib>
 #include <cstring>
 
+// NVTX ranges per phase: only in the product build (build.py defines SHRED_NVTX; nvtx3 is header-only and
+// costs a null-pointer check per call unless a profiler has injected itself)
+#ifdef SHRED_NVTX
+#include <nvtx3/nvToolsExt.h>
+namespace { struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } }; }
+#define SHRED_RANGE(name) NvtxRange shred_nvtx_range_(name)
+#else
+#define SHRED_RANGE(name) do { } while (0)
+#endif
+
 namespace shred {
 
 static inline double now_ms() {
@@ -80,6 +90,7 @@ void TrainerCore::sync_mirrors() {  // Trainer.heap in the reference's layout (r
 // ---------------------------------------------------------------------------------------------- load (bpe.cpp:110-185)
 
 int TrainerCore::load_file(const char* path) {
+  SHRED_RANGE("bpe_load_corpus");
   int fd = ::open(path, O_RDONLY);
   if (fd < 0) { std::fprintf(stderr, "[ERROR]\t Couldn't open file: %s\n", path); return -1; }  // bpe.cpp:118-122
   struct stat st;
@@ -139,6 +150,7 @@ EngineConfig TrainerCore::engine_config() const {
 }
 
 int TrainerCore::load_buffer(const uint8_t* text, size_t n) {
+  SHRED_RANGE("bpe_b200_load_buffer");
   double t0 = now_ms();
   EngineConfig ec = engine_config();
   int rc = eng_->load(text, n, ec, &info_);
@@ -173,6 +185,7 @@ int TrainerCore::finish_load(size_t n, double t0) {
 // ------------------------------------------------------------------------------------- count (bpe.cpp:187-230), init
 
 void TrainerCore::count_bigrams() {
+  SHRED_RANGE("bpe_count_bigrams");
   if (!loaded_) { sync_mirrors(); return; }
   const Rec* recs = nullptr; size_t n = 0;
   if (!quiet_) std::printf("[INFO]\t Counting bigrams from %zu words...\n", static_cast<size_t>(info_.n_words));
@@ -262,6 +275,7 @@ int TrainerCore::merge_batch(int batch_size) {  // the ABI's step-wise entry: C 
 }
 
 int TrainerCore::merge_loop(int batch_size) {
+  SHRED_RANGE("bpe_merge_batch");
   if (heap_.empty()) {  // bpe.cpp:237-240
     if (!quiet_) std::printf("[INFO]\t Heap is empty, no more merges possible\n");
     return 0;
@@ -317,6 +331,7 @@ int TrainerCore::merge_loop(int batch_size) {
 }
 
 int TrainerCore::train() {  // bpe.cpp:345-386
+  SHRED_RANGE("bpe_train");
   double t0 = now_ms();
   eng_->mark_begin();
   host_heap_ms_ = 0; occurrences_ = 0;
@@ -353,6 +368,7 @@ int TrainerCore::train() {  // bpe.cpp:345-386
 // ------------------------------------------------------------------------------------------- save (bpe.cpp:388-432)
 
 void TrainerCore::save(const char* model_path, const char* vocab_path) {
+  SHRED_RANGE("bpe_save");
   double t0 = now_ms();
   size_t M = abi_->num_merges < merge_cap_ ? abi_->num_merges : merge_cap_;
   size_t T = 256 + M;

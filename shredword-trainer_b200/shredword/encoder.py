@@ -4,6 +4,10 @@ Host-side mirror of the reference's pure-Python `BPETokenizer` (reference shredw
 (`load`, `encode`, `decode`) and error behaviour (`decode` raises ValueError on an id outside the vocabulary), but the
 model is the trainer's binary merge list (reference shredword/csrc/bpe/bpe.cpp:419-427) and words are the trainer's
 whitespace-delimited tokens (bpe.cpp:131-152) instead of regex chunks.  All work happens in libtrainer.so (CUDA, sm_100a).
+
+LOSSY with respect to whitespace: the delimiter bytes (tab, newline, carriage return, space) separate words and produce no ids,
+so decode(encode("a b")) == "ab", whereas the reference's regex chunks keep whitespace and round-trip the text.  encode_bytes
+returns CSR offsets (one row per word) for callers that want to re-insert their delimiters.
 """
 import ctypes
 import struct
