@@ -449,7 +449,7 @@ def main():
                      "phase_avg_us": {"probe_and_deltas": 1e3 * all_phase_ms / all_n if all_n else None, "fold_and_publish": 1e3 * S("fold_phase_ms") / all_n if all_n else None,
                                       "rewrite_and_new_lists": 1e3 * S("rewrite_phase_ms") / all_n if all_n else None,
                                       "what": "in-kernel %globaltimer of the timed launches; the host continues as soon as phase 2 has published"},
-                     "single_cta_launches_per_step": int(st["single_launches"])},
+                     "single_cta_merges_per_step": int(st["single_launches"]), "of_which_by_resident_server": int(st["server_merges"]), "server_starts_per_step": int(st["server_starts"])},
         "detail": {"merges_per_step": merges, "n_words": int(st["n_words"]), "n_symbols_initial": int(st["n_symbols_initial"]), "n_symbols_final": int(st["n_symbols_live"]),
                    "occurrences": int(st["occurrences"]), "pair_entries": int(st["pair_entries"]), "heap_pushes": int(st["heap_pushes"]), "heap_pops": int(st["heap_pops"]),
                    "tie_rate_upper": st["tie_root_equal"] / merges if merges else None, "tie_rate_lower": st["tie_same_as_prev"] / merges if merges else None,

@@ -123,6 +123,7 @@ typedef struct shred_stats_t {
   uint64_t tie_root_equal, tie_same_as_prev;
   double fold_phase_ms, rewrite_phase_ms; /* in-kernel timer of the timed launches: end of phase 1 -> published | -> CTA 0 done */
   uint64_t single_launches;      /* merges of the last trainer handled by the one-CTA variant of the merge kernel */
+  uint64_t server_merges, server_starts; /* of those: taken by the resident merge server (no launch) / times it was started */
 } shred_stats_t;
 SHRED_API int bpe_b200_get_stats(const Trainer* trainer, shred_stats_t* out);
 /* Debug/parity getters: copy the current word table out of HBM.  word order = reference StrMap iteration order.

@@ -139,6 +139,7 @@ class CudaEngine : public Engine {
     CK(cudaEventCreate(&ev1_));
     CK(cudaEventCreate(&evm0_));
     CK(cudaEventCreate(&evm1_));
+    CK(cudaEventCreateWithFlags(&ev_gen_, cudaEventDisableTiming));
     cudaMemPool_t pool;  // stream-ordered allocations; keep freed blocks cached so repeated loads do not pay cudaMalloc
     if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     {  // in-kernel phase timestamps (%globaltimer) of the timed launches
@@ -153,6 +154,17 @@ class CudaEngine : public Engine {
     CK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(CountStage))));
     int nb = 0;
     CK(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallStage))));
+    CK(cudaFuncSetAttribute(k_merge_server, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallStage))));
+    {
+      void* sp = nullptr;
+      CK(cudaHostAlloc(&sp, sizeof(ServerCmd) + 64, cudaHostAllocMapped));
+      std::memset(sp, 0, sizeof(ServerCmd) + 64);
+      srv_cmd_ = static_cast<ServerCmd*>(sp);
+      srv_done_ = reinterpret_cast<ServerDone*>(static_cast<uint8_t*>(sp) + sizeof(ServerCmd));
+      CK(cudaStreamCreateWithFlags(&st_srv_, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev_srv_, cudaEventDisableTiming));
+      if (const char* ns = std::getenv("SHRED_NO_SERVER")) srv_enabled_ = !(*ns && *ns != '0');
+    }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_merge<false>, 256, 0) == cudaSuccess && nb > 0) merge_ctas_per_sm_ = nb < 4 ? nb : 4;
     if (const char* w = std::getenv("SHRED_WORLD")) world_ = std::atoi(w);
     if (const char* vr = std::getenv("SHRED_VIRTUAL_RANKS")) if (std::atoi(vr) > 1) { world_ = std::atoi(vr); virtual_ = true; }
@@ -275,6 +287,7 @@ class CudaEngine : public Engine {
 
   int load_impl(const uint8_t* text, int fd, size_t n, const EngineConfig& cfg, LoadInfo* info) {
     CK(cudaSetDevice(dev_));
+    RC(srv_stop());
     cfg_ = cfg;
     vocab_hint_ = cfg.vocab_size < (1ull << 22) ? cfg.vocab_size : (1ull << 22);
     P_.unk_id = cfg.unk_id;
@@ -300,7 +313,33 @@ class CudaEngine : public Engine {
       CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
       bar_count_ = 0;
       pre.valid = true;
-      if (stream_file(fd, n, d_text, &pre) != 0) { free_wt(pre.wt); cudaFreeAsync(d_text, st_); return -1; }
+      // First load of a process: the stream-ordered pool is still small and every later allocation of the ingest (symbols, word
+      // indices, occurrence lists: ~0.6 B per corpus byte) would grow it on the critical path (0.78 s at 10 GB).  Grow it now, on a
+      // helper thread and stream, while the file is on its way over PCIe.
+      std::thread warm;
+      {
+        cudaMemPool_t pool; uint64_t reserved = 0, used = 0; size_t free_b = 0, total_b = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+          uint64_t want = n - n / 4, idle = reserved > used ? reserved - used : 0;
+          if (want > free_b / 3) want = free_b / 3;
+          if (want > idle + (256ull << 20)) {
+            const uint64_t grow = want - idle;
+            const int dev = dev_;
+            warm = std::thread([grow, dev]() {
+              cudaSetDevice(dev);
+              cudaStream_t sa; void* p = nullptr;
+              if (cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking) != cudaSuccess) return;
+              if (cudaMallocAsync(&p, grow, sa) == cudaSuccess) cudaFreeAsync(p, sa);
+              cudaStreamSynchronize(sa);
+              cudaStreamDestroy(sa);
+            });
+          }
+        }
+      }
+      const int src = stream_file(fd, n, d_text, &pre);
+      if (warm.joinable()) warm.join();
+      if (src != 0) { free_wt(pre.wt); cudaFreeAsync(d_text, st_); return -1; }
     } else {
       CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
     }
@@ -608,6 +647,7 @@ class CudaEngine : public Engine {
   // --------------------------------------------------------------------------------------------------------- count
   int count_pairs(const Rec** recs, size_t* n) override {
     CK(cudaSetDevice(dev_));
+    RC(srv_stop());
     *recs = out_.data(); *n = 0;
     if (!loaded_) return 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
@@ -677,6 +717,64 @@ class CudaEngine : public Engine {
     return -1;
   }
 
+  // ------------------------------------------------------------------------------------------------- merge server
+  // (kernels_merge.cuh k_merge_server.)  The server reads symbols, lists and tables that every other kernel of the engine also
+  // writes, so the host keeps them apart: it waits for the server's "phase 3 done" before it launches anything else on the data
+  // (srv_quiesce), makes the server wait for the engine's stream when it starts (event), waits for the last general merge kernel
+  // to finish before it hands the server a command, and stops the server before buffers move or a run of merges ends.
+  int srv_start() {
+    if (srv_alive_) return 0;
+    CK(cudaEventRecord(ev_srv_, st_));
+    CK(cudaStreamWaitEvent(st_srv_, ev_srv_, 0));
+    MergeArgs ma; std::memset(&ma, 0, sizeof ma);
+    ma.ids = ids_; ma.ids_cap = ids_cap_; ma.wid = wid_; ma.wcnt = wcnt_; ma.pool = pool_; ma.pool_cap = pool_cap_; ma.sc = sc_;
+    ma.P = P_; ma.dt = dt_; ma.pt = pt_; ma.ctr = ctr_; ma.recs = recs_; ma.rec_cap = rec_cap_; ma.ctrl = ctrl_; ma.dbg = dbg_; ma.D = dist_;
+    std::memset(srv_cmd_, 0, sizeof(ServerCmd));
+    srv_done_->w[0] = 0; srv_done_->w[1] = 0;
+    ++srv_seq_;  // sequence numbers never repeat, so a stale command block can never be taken for a new command
+    k_merge_server<<<1, 1024, sizeof(SmallStage), st_srv_>>>(ma, srv_cmd_, srv_done_, srv_seq_);
+    CK(cudaGetLastError());
+    launches_++; srv_starts_++;
+    srv_alive_ = true; srv_busy_ = false;
+    return 0;
+  }
+  void srv_write(uint32_t op, int32_t a, int32_t b, int32_t n, uint32_t serial, uint32_t lenA, uint32_t lenB, uint32_t list_len, uint32_t tag, bool timed) {
+    volatile ull* w = srv_cmd_->w;
+    const ull seq = (srv_seq_ & 0xFFFFFFFFull) << 32;
+    const ull d0[4] = {static_cast<uint32_t>(a) | (static_cast<ull>(static_cast<uint32_t>(b)) << 32), static_cast<uint32_t>(n) | (static_cast<ull>(serial) << 32),
+                       list_len | (static_cast<ull>(tag) << 32), timed ? 1ull : 0ull};
+    const ull d1[4] = {op, lenA, lenB, 0};
+    for (int q = 0; q < 4; q++) { w[2 * q] = d0[q]; __atomic_store_n(&w[2 * q + 1], d1[q] | seq, __ATOMIC_RELEASE); }  // a quarter's tag goes last
+  }
+  bool srv_exited() const { return static_cast<uint32_t>(__atomic_load_n(&srv_done_->w[0], __ATOMIC_ACQUIRE) >> 32) == 2u; }
+  // wait until the server has finished phase 3 of the last merge it was given
+  int srv_quiesce() {
+    if (!srv_alive_ || !srv_busy_) return 0;
+    const double t0 = now_ms();
+    uint64_t spins = 0;
+    for (;;) {
+      const ull d = __atomic_load_n(&srv_done_->w[0], __ATOMIC_ACQUIRE);
+      if (static_cast<uint32_t>(d) == srv_tag_ && static_cast<uint32_t>(d >> 32) == 1u) break;
+      if (static_cast<uint32_t>(d >> 32) == 2u) break;  // it has left: everything it did is complete
+      if ((++spins & 0xFFFF) == 0 && now_ms() - t0 > 30000.0) { std::fprintf(stderr, "[ERROR]\t merge server does not answer\n"); return -1; }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    srv_busy_ = false;
+    return 0;
+  }
+  int srv_stop() {
+    if (!srv_alive_) return 0;
+    int rc = srv_quiesce();
+    if (!srv_exited()) srv_write(SRV_OP_QUIT, 0, 0, 0, 0, 0, 0, 0, 0, false);
+    if (cudaStreamSynchronize(st_srv_) != cudaSuccess) rc = -1;  // the kernel has left (it also leaves by itself after SERVER_IDLE_NS)
+    srv_alive_ = false; srv_busy_ = false;
+    return rc;
+  }
+  void begin_merges() override {}
+  void end_merges() override { srv_stop(); }
+
   // --------------------------------------------------------------------------------------------------------- merge
   int merge(int32_t a, int32_t b, int32_t new_id, uint32_t serial, uint32_t list_len, const Rec** recs, size_t* n, uint64_t* occurrences) override {
     *recs = out_.data(); *n = 0; *occurrences = 0;
@@ -691,9 +789,9 @@ class CudaEngine : public Engine {
     tok_len_[new_id] = lenA + lenB;
     // keep the pair table at most half full even if this merge creates every key it can (4 per distinct id)
     const uint64_t worst_new = 4ull * (static_cast<uint64_t>(new_id) + 2);
-    if ((pt_n_ + worst_new) * 2 > pt_.cap) RC(grow_pt(pt_n_ + worst_new));
-    if (worst_new * 2 > dt_.cap) RC(alloc_dt(next_pow2(worst_new * 2)));
-    RC(ensure_scratch(list_len));
+    if ((pt_n_ + worst_new) * 2 > pt_.cap) { RC(srv_stop()); RC(grow_pt(pt_n_ + worst_new)); }   // buffers move: the server holds their addresses
+    if (worst_new * 2 > dt_.cap) { RC(srv_stop()); RC(alloc_dt(next_pow2(worst_new * 2))); }
+    if (list_len > sc_.cap) { RC(srv_stop()); RC(ensure_scratch(list_len)); }
     const bool timed = timing_every_ > 0 && (merge_seq_++ % timing_every_) == 0;
     const bool profiled = !profile_merges_.empty() && std::find(profile_merges_.begin(), profile_merges_.end(), merge_no_) != profile_merges_.end();
     if (profiled) { cudaStreamSynchronize(st_); cudaProfilerStart(); }
@@ -702,9 +800,29 @@ class CudaEngine : public Engine {
     // again if the small one had to give up (ERR_RETRY: it has not changed anything then)
     bool small = world_ == 1 && force_grid_ <= 0 && list_len <= small_max_ && ids_cap_ < (1ull << 30);
     int grid = 1;
+    double srv_ms = 0;
     for (;;) {
       const double tl0 = now_ms();
       ++flag_;
+      if (small && srv_enabled_) {  // hand the merge to the resident CTA: no launch
+        if (srv_alive_ && srv_exited()) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; }  // it left after an idle period
+        if (general_pending_) { CK(cudaEventSynchronize(ev_gen_)); general_pending_ = false; }  // the last cooperative merge kernel (its phase 3) has finished
+        RC(srv_start());
+        RC(srv_quiesce());  // one command at a time
+        srv_write(SRV_OP_MERGE, a, b, new_id, serial, lenA, lenB, list_len, static_cast<uint32_t>(flag_), timed);
+        srv_tag_ = static_cast<uint32_t>(flag_); srv_busy_ = true;
+        launch_ms_ += now_ms() - tl0;
+        const int wrc = wait_flag();
+        if (wrc == 2) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; continue; }  // the server left just before the command: start it again
+        if (wrc != 0) return wrc;
+        ++srv_seq_;
+        srv_ms = now_ms() - tl0;
+        srv_merges_++;
+        if (cv_.err & ERR_RETRY) { small = false; small_retries_++; continue; }
+        single_launches_++;
+        break;
+      }
+      RC(srv_quiesce());  // a kernel launch on the same data: the server must have finished its rewrite
       if (!small) ++pass_;
       if (timed) CK(cudaEventRecord(ev0_, st_));
       grid = small ? 1 : merge_grid(list_len);
@@ -729,6 +847,7 @@ class CudaEngine : public Engine {
           void* args[] = {&ma};
           const void* kfn = world_ > 1 ? reinterpret_cast<const void*>(k_merge<true>) : reinterpret_cast<const void*>(k_merge<false>);
           CK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, 0, st_));
+          if (srv_enabled_) { CK(cudaEventRecord(ev_gen_, st_)); general_pending_ = true; }
         }
       }
       if (timed) CK(cudaEventRecord(ev1_, st_));
@@ -747,8 +866,13 @@ class CudaEngine : public Engine {
     if (cv_.err) { std::fprintf(stderr, "[ERROR]\t device merge pass failed (err=%u)\n", cv_.err); return -1; }
     if (timed) {
       float ms = 0;
-      CK(cudaEventSynchronize(ev1_));
-      cudaEventElapsedTime(&ms, ev0_, ev1_);
+      if (srv_ms > 0) {  // handled by the resident server: command written -> control block seen, on the host clock; phase timers valid once phase 3 is done
+        ms = static_cast<float>(srv_ms);
+        RC(srv_quiesce());
+      } else {
+        CK(cudaEventSynchronize(ev1_));
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+      }
       // algorithmic bytes of the scan formulation: 4 B x (live symbols + unique words) -- n_live_ counts both
       const double algo = 4.0 * static_cast<double>(n_live_), touched = 36.0 * static_cast<double>(cv_.list_len) + 88.0 * static_cast<double>(cv_.occ_local);
       es_.scan_launches++; es_.scan_device_ms += ms; es_.scan_bytes += algo; es_.scan_bytes_touched += touched;
@@ -775,6 +899,7 @@ class CudaEngine : public Engine {
   // ---------------------------------------------------------------------------------------------------------- save
   int token_freqs(uint64_t* freq, size_t T) override {
     CK(cudaSetDevice(dev_));
+    RC(srv_stop());
     if (!loaded_ || (!n_words_ && world_ == 1) || !T) return 0;
     ull* d = nullptr;
     CK(cudaMallocAsync(reinterpret_cast<void**>(&d), T * 8, st_));
@@ -809,6 +934,7 @@ class CudaEngine : public Engine {
   }
   int get_words(uint64_t* counts, uint64_t* off, int32_t* ids, uint64_t ids_cap) override {
     if (!loaded_) return -1;
+    RC(srv_stop());
     CK(cudaStreamSynchronize(st_));
     const uint32_t N = n_words_;
     std::vector<ull> ho(N + 1);
@@ -834,6 +960,7 @@ class CudaEngine : public Engine {
   }
   uint64_t get_pairs(int32_t* ab, uint64_t* freq, uint64_t cap) override {
     if (!pt_.ent) return 0;
+    srv_stop();
     cudaStreamSynchronize(st_);
     std::vector<PairEnt> e(pt_.cap);
     if (cudaMemcpy(e.data(), pt_.ent, pt_.cap * sizeof(PairEnt), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
@@ -855,7 +982,7 @@ class CudaEngine : public Engine {
     *out = es_;
     out->n_slots = n_slots_; out->n_symbols_live = n_live_ >= n_words_ ? n_live_ - n_words_ : 0; out->pair_entries = pt_n_;
     out->kernel_launches = launches_; out->wait_ms = wait_ms_; out->launch_ms = launch_ms_; out->merge_ms = merge_ms_;
-    out->list_entries = list_entries_total_; out->pool_entries = cv_.pool_top; out->single_launches = single_launches_;
+    out->list_entries = list_entries_total_; out->pool_entries = cv_.pool_top; out->single_launches = single_launches_; out->server_merges = srv_merges_; out->server_starts = srv_starts_;
   }
   const char* name() override { return name_; }
 
@@ -870,7 +997,7 @@ class CudaEngine : public Engine {
   static constexpr uint32_t DENSE_LIST = 1u << 16;
   int merge_grid(uint32_t list_len) const {
     if (force_grid_ > 0) return force_grid_;
-    const uint64_t ctas = (static_cast<uint64_t>(list_len) + 255) / 256, maxg = static_cast<uint64_t>(n_sm_) * merge_ctas_per_sm_;
+    const uint64_t ctas = (static_cast<uint64_t>(list_len) + 255) / 256, maxg = static_cast<uint64_t>(n_sm_ - (srv_enabled_ ? 1 : 0)) * merge_ctas_per_sm_;  // one SM may hold the merge server
     return static_cast<int>(ctas < 1 ? 1 : (ctas < maxg ? ctas : maxg));
   }
 
@@ -885,6 +1012,14 @@ class CudaEngine : public Engine {
     for (int blk = 0; blk < 4; blk++) {
       while (!fresh(blk)) {
         if ((++spins & 0x3FFF) == 0) {
+          if (srv_busy_) {  // the pass was handed to the merge server
+            if (srv_exited()) {  // it left (idle period) -- before or after taking the command?
+              if (fresh(blk)) continue;
+              if (static_cast<uint32_t>(__atomic_load_n(&srv_done_->w[1], __ATOMIC_ACQUIRE)) == static_cast<uint32_t>(srv_seq_)) return 2;  // it left still waiting for this command's number: it never saw the command
+            }
+            if (now_ms() - t0 > 120000.0) { std::fprintf(stderr, "[ERROR]\t merge server timed out\n"); return -1; }
+            continue;
+          }
           cudaError_t q = cudaStreamQuery(st_);
           if (q == cudaSuccess) { if (fresh(blk)) break; std::fprintf(stderr, "[ERROR]\t device pass finished without publishing its result\n"); return -1; }
           if (q != cudaErrorNotReady) { std::fprintf(stderr, "[ERROR]\t CUDA: %s\n", cudaGetErrorString(q)); return -1; }
@@ -944,6 +1079,7 @@ class CudaEngine : public Engine {
   }
   void release_all() {
     cudaSetDevice(dev_);
+    srv_stop();
     if (dbg_print_ && dbg_n_) {
       if (small_n_) std::fprintf(stderr, "[KTIME]\t of which %llu k_merge_small launches: probe+deltas %.1f us, fold+publish %.1f us | kernel (events) %.1f us\n", (unsigned long long)small_n_,
                                  1e3 * small_acc_[0] / small_n_, 1e3 * small_acc_[1] / small_n_, 1e3 * small_acc_[2] / small_n_);
@@ -963,6 +1099,10 @@ class CudaEngine : public Engine {
     if (st_) cudaStreamSynchronize(st_);
     if (st_copy_) { cudaStreamDestroy(st_copy_); st_copy_ = nullptr; }
     dist_teardown();
+    if (srv_cmd_) cudaFreeHost(srv_cmd_);
+    if (st_srv_) cudaStreamDestroy(st_srv_);
+    if (ev_srv_) cudaEventDestroy(ev_srv_);
+    if (ev_gen_) cudaEventDestroy(ev_gen_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (evm0_) cudaEventDestroy(evm0_);
@@ -1003,6 +1143,13 @@ class CudaEngine : public Engine {
   std::vector<Rec> out_;      // the records of the last pass, decoded for the caller
   Ctrl* ctrl_ = nullptr;
   struct CtrlView { uint32_t n_recs = 0, err = 0, list_len = 0, occ_local = 0, n_keys = 0; uint64_t occ = 0, pt_n = 0, pool_top = 0; } cv_;
+  ServerCmd* srv_cmd_ = nullptr;
+  ServerDone* srv_done_ = nullptr;
+  cudaStream_t st_srv_ = nullptr;
+  cudaEvent_t ev_srv_ = nullptr, ev_gen_ = nullptr;
+  bool srv_enabled_ = true, srv_alive_ = false, srv_busy_ = false, general_pending_ = false;
+  uint64_t srv_seq_ = 0, srv_merges_ = 0, srv_starts_ = 0;
+  uint32_t srv_tag_ = 0;
   uint32_t small_max_ = SMALL_MAX;
   uint64_t single_launches_ = 0, small_retries_ = 0;
   DevCounters* ctr_ = nullptr;

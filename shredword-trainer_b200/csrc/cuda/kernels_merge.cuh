@@ -218,17 +218,22 @@ __device__ __forceinline__ bool small_add_probe(SmallStage& s, const MergeArgs& 
   return false;
 }
 
-__global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const uint32_t slots) {
-  extern __shared__ __align__(16) unsigned char small_smem[];
-  SmallStage& s = *reinterpret_cast<SmallStage*>(small_smem);
+__device__ __forceinline__ void small_clear(SmallStage& s, uint32_t slots, ull empty) {
+  for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) { s.key[i] = empty; s.lo[i] = 0u; s.hi[i] = 0u; s.seq[i] = 0xFFFFFFFFu; s.nocc[i] = 0u; }
+  if (threadIdx.x == 0) { s.n_keys = 0; s.n_occ = 0; s.n_recs = 0; s.overflow = 0; s.pt_after = 0ull; s.pool_after = 0ull; }
+}
+// the whole merge in one CTA (all threads of the block call it); returns false if it gave the merge up (ERR_RETRY published).
+// PRECLEARED: the shared tables are already clean and a block barrier has passed since (the resident server cleans up after every
+// merge, off the critical path) -- ncu's stall samples put 15 % of a launch into that first barrier.
+template <bool PRECLEARED>
+__device__ __forceinline__ bool small_merge_body(SmallStage& s, const MergeArgs& a, const uint32_t slots) {
   const uint32_t t = threadIdx.x, lane = t & 31u, nt = blockDim.x, mask = slots - 1u;
   DevCounters* const ctr = a.ctr;
   const ull empty = a.dt.empty;
   if (t == 0 && a.dbg) a.dbg[0] = gtime();
   const ListRef lr = a.pt.lists[a.serial];  // in flight while the tables are cleared
-  for (uint32_t i = t; i < slots; i += nt) { s.key[i] = empty; s.lo[i] = 0u; s.hi[i] = 0u; s.seq[i] = 0xFFFFFFFFu; s.nocc[i] = 0u; }
-  if (t == 0) { s.n_keys = 0; s.n_occ = 0; s.n_recs = 0; s.overflow = 0; s.pt_after = 0ull; s.pool_after = 0ull; }
-  __syncthreads();
+  if (t == nt - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(&a.pt.ent[mix64(fc_key(a.A, a.B)) & a.pt.mask]));  // phase 2 zeroes the merged pair's frequency there
+  if (!PRECLEARED) { small_clear(s, slots, empty); __syncthreads(); }
   // ---- phase 1: one list entry per thread
   if (t < lr.len && lr.len <= nt) {
     const PoolEnt e = a.pool[lr.off + t];
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const u
   if (t == 0 && a.dbg) a.dbg[1] = gtime();
   if (s.overflow || lr.len > nt) {  // nothing in global memory has been touched: hand the merge to the general kernel
     if (t == 0) wire_ctrl(a.ctrl, a.tag, 0u, ERR_RETRY, lr.len, 0u, 0ull, 0u, 0ull, 0ull);
-    return;
+    return false;
   }
   // ---- phase 2: fold, 32 keys per warp at a time
   const uint32_t n_keys = s.n_keys, n_occ = s.n_occ;
@@ -314,9 +319,9 @@ __global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const u
     for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pre, o2); if (lane >= static_cast<uint32_t>(o2)) pre += y; }
     const uint32_t pool_need = __shfl_sync(0xFFFFFFFFu, pre, 31);
     ull b_pt = 0, b_pool = 0;
-    if (lane == 0) {
-      if (m_new) { b_pt = atomicAdd(&ctr->pt_n, static_cast<ull>(__popc(m_new))); atomicMax(&s.pt_after, b_pt + __popc(m_new)); }
-      if (pool_need) { b_pool = atomicAdd(&ctr->pool_top, static_cast<ull>(pool_need)); atomicMax(&s.pool_after, b_pool + pool_need); }
+    if (lane == 0) {  // both reservations in flight before either result is used
+      if (m_new) b_pt = atomicAdd(&ctr->pt_n, static_cast<ull>(__popc(m_new)));
+      if (pool_need) b_pool = atomicAdd(&ctr->pool_top, static_cast<ull>(pool_need));
     }
     // now the pair table's answers
     if (normal && !is_new) {
@@ -340,6 +345,10 @@ __global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const u
     const uint32_t m_emit = __ballot_sync(0xFFFFFFFFu, emit);
     uint32_t b_rec = 0;
     if (lane == 0 && m_emit) b_rec = atomicAdd(&s.n_recs, static_cast<uint32_t>(__popc(m_emit)));
+    if (lane == 0) {
+      if (m_new) atomicMax(&s.pt_after, b_pt + __popc(m_new));
+      if (pool_need) atomicMax(&s.pool_after, b_pool + pool_need);
+    }
     b_rec = __shfl_sync(0xFFFFFFFFu, b_rec, 0);
     b_pt = __shfl_sync(0xFFFFFFFFu, b_pt, 0); b_pool = __shfl_sync(0xFFFFFFFFu, b_pool, 0);
     if (is_new) { serial = static_cast<uint32_t>(b_pt) + __popc(m_new & lt); a.pt.ent[sl].serial = serial; }
@@ -381,6 +390,76 @@ __global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const u
     if (b2 != NO_LIST) { ne.pos = x.x; a.pool[b2 + y.y] = ne; }
   }
   if (t == 0 && a.dbg) a.dbg[3] = gtime();
+  return true;
+}
+__global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const uint32_t slots) {
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  small_merge_body<false>(*reinterpret_cast<SmallStage*>(small_smem), a, slots);
+}
+
+// ------------------------------------------------------------------------------------------------ resident merge server
+// A launch costs the host ~3 us of API time and the device ~3-5 us before the first instruction runs, with a cold instruction
+// cache -- as much as the work of a short merge itself.  While the host replays its heap, ONE CTA therefore stays resident
+// (k_merge_server, 1024 threads, its own stream) and takes short merges as 64-byte commands from mapped host memory: the host
+// writes (A, B, N, lengths, serial, list length, tag), the CTA polls the block (one PCIe read round trip per poll, all four
+// 16-byte quarters in flight together; a command is accepted when the sequence number in its first and last quarter agree),
+// runs small_merge_body and reports the end of phase 3 in a second self-validating block, after which the host may run other
+// kernels on the data.  The server leaves when told to (end of bpe_merge_batch / bpe_train, any other operation) or after
+// SERVER_IDLE_NS without a command -- it can never outlive a dead host by more than that.
+// Command block: four 16-byte quarters {data (64 bits), data (32 bits) | sequence number << 32}; the host writes a quarter's first
+// word before its second, the device reads a quarter with one 16-byte load and accepts a command only when all four carry the
+// sequence number it expects (so neither a half-written quarter nor quarters of two different commands can be taken for one).
+//   q0: A | B << 32, op      q1: N | serial << 32, lenA      q2: list_len | tag << 32, lenB      q3: timed, -
+struct ServerCmd { ull w[8]; };
+struct ServerDone { ull w[2]; }; // w0 = tag | state << 32 (1 = phase 3 of that merge finished, 2 = server has left), w1 = sequence number it waits for
+constexpr ull SERVER_IDLE_NS = 300000000ull;  // 0.3 s
+enum : uint32_t { SRV_OP_MERGE = 1, SRV_OP_QUIT = 2 };
+__global__ void __launch_bounds__(1024) k_merge_server(MergeArgs a, const ServerCmd* cmd, ServerDone* done, ull first_seq) {
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  SmallStage& s = *reinterpret_cast<SmallStage*>(small_smem);
+  __shared__ ull c[8];
+  __shared__ uint32_t op;
+  ull* const dbg = a.dbg;
+  ull next = first_seq;
+  small_clear(s, SMALL_SLOTS_MAX, a.dt.empty);  // the poll loop's barrier below separates this from the first merge
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const ull t0 = gtime();
+      op = SRV_OP_QUIT;
+      for (;;) {
+        ull q[8];
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[0]), "=l"(q[1]) : "l"(&cmd->w[0]));
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[2]), "=l"(q[3]) : "l"(&cmd->w[2]));
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[4]), "=l"(q[5]) : "l"(&cmd->w[4]));
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[6]), "=l"(q[7]) : "l"(&cmd->w[6]));
+        const ull want = next & 0xFFFFFFFFull;
+        if ((q[1] >> 32) == want && (q[3] >> 32) == want && (q[5] >> 32) == want && (q[7] >> 32) == want) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) c[k] = q[k];
+          op = static_cast<uint32_t>(q[1] & 0xFFFFFFFFull);
+          break;
+        }
+        if (gtime() - t0 > SERVER_IDLE_NS) break;  // nobody is talking to us any more
+      }
+    }
+    __syncthreads();
+    if (op != SRV_OP_MERGE) break;
+    __threadfence();  // drop this SM's L1: other kernels may have rewritten symbols, lists and tables since the last command
+    a.A = static_cast<int32_t>(c[0] & 0xFFFFFFFFull); a.B = static_cast<int32_t>(c[0] >> 32);
+    a.N = static_cast<int32_t>(c[2] & 0xFFFFFFFFull); a.serial = static_cast<uint32_t>(c[2] >> 32);
+    a.lenA = static_cast<uint32_t>(c[3] & 0xFFFFFFFFull); a.lenB = static_cast<uint32_t>(c[5] & 0xFFFFFFFFull);
+    const uint32_t list_len = static_cast<uint32_t>(c[4] & 0xFFFFFFFFull);
+    a.tag = static_cast<uint32_t>(c[4] >> 32);
+    a.dbg = c[6] ? dbg : nullptr;
+    const uint32_t slots = small_slots_for(list_len);
+    small_merge_body<true>(s, a, slots);
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); st_wire(&done->w[0], a.tag | (1ull << 32), next); }  // phase 3 is complete and visible to later kernels
+    ++next;
+    small_clear(s, slots, a.dt.empty);  // for the next merge, while the host is busy with this one's records
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { __threadfence(); st_wire(&done->w[0], 0xFFFFFFFFull | (2ull << 32), next); }
 }
 
 __global__ void k_rehash(PairTable oldt, PairTable newt, DevCounters* ctr) {

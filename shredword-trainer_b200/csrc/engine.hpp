@@ -61,6 +61,7 @@ struct EngineStats {
   double fold_phase_ms, rewrite_phase_ms;  // same timer: phase 1 end -> published (phase 2) -> CTA 0 done (phase 3), all timed launches
   uint64_t list_entries, pool_entries;   // occurrence-list entries probed by all merges / entries allocated in the pool
   uint64_t single_launches;              // merges handled by the one-CTA variant of the kernel
+  uint64_t server_merges, server_starts; // of those: taken by the resident merge server (no launch) / times the server was started
   uint64_t count_launches; double count_device_ms; double count_bytes;
   double fill_device_ms, fill_bytes;     // count pass, second half: fold + initial occurrence lists
   uint64_t ingest_launches; double ingest_device_ms; double ingest_bytes;
@@ -85,6 +86,10 @@ class Engine {
   // serial / list_len: the pair's dense id and the length of its occurrence list, both as reported by the PUSH record that
   // created its heap entry (rec_list_len()); they let the device find the list with one load and size its grid.
   virtual int merge(int32_t a, int32_t b, int32_t new_id, uint32_t serial, uint32_t list_len, const Rec** recs, size_t* n, uint64_t* occurrences) = 0;
+  // Brackets of a run of merge() calls (bpe_merge_batch / bpe_train): lets an engine keep state resident between the merges
+  // of a run (the CUDA engine's merge server) and guarantees it is gone when the run's entry point returns.
+  virtual void begin_merges() {}
+  virtual void end_merges() {}
   // freq[id] += word_count over all live symbols with 0 <= id < n_tokens (reference bpe.cpp:409-415).
   virtual int token_freqs(uint64_t* freq, size_t n_tokens) = 0;
   virtual int word_counts(uint64_t* out) = 0;  // host mirror of Corpus.word_counts

@@ -281,6 +281,7 @@ int TrainerCore::merge_loop(int batch_size) {
     return 0;
   }
   int done = 0;
+  struct MergeRun { Engine* e; explicit MergeRun(Engine* x) : e(x) { e->begin_merges(); } ~MergeRun() { e->end_merges(); } } run(eng_);
   // host time between two device merges (pops until a current entry, then the records of the merge): two clock reads per
   // merge -- one per pop (~56 stale pops per merge) cost 2.5 us per merge in clock calls alone
   double h_open = now_ms();
@@ -423,7 +424,7 @@ void TrainerCore::get_stats(shred_stats_t* s) {
   s->wait_ms = es.wait_ms; s->launch_ms = es.launch_ms; s->save_wall_ms = save_wall_ms_;
   s->h2d_bytes = es.h2d_bytes; s->d2h_bytes = es.d2h_bytes;
   s->tie_root_equal = tie_root_equal_; s->tie_same_as_prev = tie_same_as_prev_;
-  s->fold_phase_ms = es.fold_phase_ms; s->rewrite_phase_ms = es.rewrite_phase_ms; s->single_launches = es.single_launches;
+  s->fold_phase_ms = es.fold_phase_ms; s->rewrite_phase_ms = es.rewrite_phase_ms; s->single_launches = es.single_launches; s->server_merges = es.server_merges; s->server_starts = es.server_starts;
 }
 
 }  // namespace shred

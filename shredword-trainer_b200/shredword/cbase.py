@@ -71,7 +71,7 @@ class Stats(Structure):  # include/shred_abi.h shred_stats_t
                [(n, c_double) for n in ("load_wall_ms", "h2d_ms", "train_wall_ms", "host_heap_ms", "wait_ms", "save_wall_ms", "train_device_ms", "launch_ms", "scan_bytes_touched")] + \
                [("dense_launches", c_uint64), ("dense_device_ms", c_double), ("dense_bytes", c_double), ("scan_phase_ms", c_double), ("dense_phase_ms", c_double)] + \
                [("h2d_bytes", c_uint64), ("d2h_bytes", c_uint64), ("tie_root_equal", c_uint64), ("tie_same_as_prev", c_uint64),
-                ("fold_phase_ms", c_double), ("rewrite_phase_ms", c_double), ("single_launches", c_uint64)]
+                ("fold_phase_ms", c_double), ("rewrite_phase_ms", c_double), ("single_launches", c_uint64), ("server_merges", c_uint64), ("server_starts", c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
