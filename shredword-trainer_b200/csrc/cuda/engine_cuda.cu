@@ -526,6 +526,7 @@ class CudaEngine : public Engine {
     CK(cudaGetLastError());
     es_.d2h_bytes += 256 * 8 + 8 + sizeof(DevCounters);
     charset_keep(info->hist, cfg_.coverage, info->keep, &info->n_distinct, &info->n_keep);
+    std::memcpy(keep_, info->keep, 256);
     info->n_symbols = S1 - N;
     uint32_t lo = 0, n_local = N;
     host_counts_.clear();
@@ -574,6 +575,7 @@ class CudaEngine : public Engine {
     // --- pair/delta tables sized for this trainer
     RC(alloc_tables());
     loaded_ = true;
+    fresh_ = true;  // every token is still a single byte
     return 0;
   }
 
@@ -662,8 +664,22 @@ class CudaEngine : public Engine {
       CK(cudaEventRecord(ev0_, st_));
       const uint32_t n4c = static_cast<uint32_t>((n_slots_ + 3) / 4);
       if (n_words_) {
-        k_count<<<n_sm_ * 4, 256, sizeof(CountStage), st_>>>(reinterpret_cast<const int4*>(ids_), reinterpret_cast<const uint4*>(wid_), n4c, wcnt_, P_, dt_, ctr_,
-                                                             world_ > 1 ? seq_base(rank_) : 0ull);
+        // fresh corpus with few distinct bytes: direct-indexed shared-memory tables (k_count_dense); otherwise the hashed ones
+        uint32_t K = 0;
+        ByteLut lut;
+        if (fresh_ && !std::getenv("SHRED_COUNT_HASHED")) {
+          for (int bv = 0; bv < 256; bv++) lut.code[bv] = (keep_[bv] && bv != P_.unk_code) ? static_cast<uint8_t>(K++) : static_cast<uint8_t>(0xFF);
+        }
+        const size_t dense_bytes = static_cast<size_t>(K) * K * 16;
+        if (K > 0 && K < 255 && dense_bytes <= (196u << 10)) {
+          const int per_sm = std::max<int>(1, std::min<int>(4, static_cast<int>((200u << 10) / (dense_bytes + 1024))));
+          CK(cudaFuncSetAttribute(k_count_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dense_bytes)));
+          k_count_dense<<<n_sm_ * per_sm, 256, dense_bytes, st_>>>(reinterpret_cast<const int4*>(ids_), reinterpret_cast<const uint4*>(wid_), n4c, wcnt_, lut, K, dt_, ctr_,
+                                                                   world_ > 1 ? seq_base(rank_) : 0ull);
+        } else {
+          k_count<<<n_sm_ * 4, 256, sizeof(CountStage), st_>>>(reinterpret_cast<const int4*>(ids_), reinterpret_cast<const uint4*>(wid_), n4c, wcnt_, P_, dt_, ctr_,
+                                                               world_ > 1 ? seq_base(rank_) : 0ull);
+        }
         launches_++;
       }
       CK(cudaEventRecord(ev1_, st_));
@@ -736,8 +752,12 @@ class CudaEngine : public Engine {
     CK(cudaGetLastError());
     launches_++; srv_starts_++;
     srv_alive_ = true; srv_busy_ = false;
+    live_servers().fetch_add(1);
     return 0;
   }
+  // merge servers resident on the device on behalf of trainers of this process: each holds one SM that a cooperative launch of
+  // any of those trainers must not count on
+  static std::atomic<int>& live_servers() { static std::atomic<int> n{0}; return n; }
   void srv_write(uint32_t op, int32_t a, int32_t b, int32_t n, uint32_t serial, uint32_t lenA, uint32_t lenB, uint32_t list_len, uint32_t tag, bool timed) {
     volatile ull* w = srv_cmd_->w;
     const ull seq = (srv_seq_ & 0xFFFFFFFFull) << 32;
@@ -770,6 +790,7 @@ class CudaEngine : public Engine {
     if (!srv_exited()) srv_write(SRV_OP_QUIT, 0, 0, 0, 0, 0, 0, 0, 0, false);
     if (cudaStreamSynchronize(st_srv_) != cudaSuccess) rc = -1;  // the kernel has left (it also leaves by itself after SERVER_IDLE_NS)
     srv_alive_ = false; srv_busy_ = false;
+    live_servers().fetch_sub(1);
     return rc;
   }
   void begin_merges() override {}
@@ -784,6 +805,7 @@ class CudaEngine : public Engine {
       std::fprintf(stderr, "[ERROR]\t merge of an unknown token or pair (%d,%d)\n", a, b);
       return -1;
     }
+    fresh_ = false;
     if (static_cast<size_t>(new_id) >= tok_len_.size()) tok_len_.resize(static_cast<size_t>(new_id) + 1, 1u);
     const uint32_t lenA = tok_len_[a], lenB = tok_len_[b];
     tok_len_[new_id] = lenA + lenB;
@@ -805,7 +827,7 @@ class CudaEngine : public Engine {
       const double tl0 = now_ms();
       ++flag_;
       if (small && srv_enabled_) {  // hand the merge to the resident CTA: no launch
-        if (srv_alive_ && srv_exited()) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; }  // it left after an idle period
+        if (srv_alive_ && srv_exited()) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; live_servers().fetch_sub(1); }  // it left after an idle period
         if (general_pending_) { CK(cudaEventSynchronize(ev_gen_)); general_pending_ = false; }  // the last cooperative merge kernel (its phase 3) has finished
         RC(srv_start());
         RC(srv_quiesce());  // one command at a time
@@ -813,7 +835,7 @@ class CudaEngine : public Engine {
         srv_tag_ = static_cast<uint32_t>(flag_); srv_busy_ = true;
         launch_ms_ += now_ms() - tl0;
         const int wrc = wait_flag();
-        if (wrc == 2) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; continue; }  // the server left just before the command: start it again
+        if (wrc == 2) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; live_servers().fetch_sub(1); continue; }  // the server left just before the command: start it again
         if (wrc != 0) return wrc;
         ++srv_seq_;
         srv_ms = now_ms() - tl0;
@@ -882,11 +904,14 @@ class CudaEngine : public Engine {
       dbg_acc_[0] += p1; dbg_acc_[1] += p2; dbg_acc_[2] += p3; dbg_acc_[3] += ms; dbg_n_++;
       if (small) { small_acc_[0] += p1; small_acc_[1] += p2; small_acc_[2] += ms; small_n_++; }
       if (dbg_print_ && (dbg_n_ % 500) == 0)
-        std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
+        std::fprintf(stderr, "[KTIME]\t decoding the records of all merges took the host %.1f ms\n", fetch_ms_);
+      std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
                      (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
     }
     list_entries_total_ += cv_.list_len;
+    const double tf0 = dbg_print_ ? now_ms() : 0.0;
     RC(fetch_records());
+    if (dbg_print_) fetch_ms_ += now_ms() - tf0;
     *recs = out_.data();
     *n = out_.size(); *occurrences = cv_.occ;
     pt_n_ = cv_.pt_n;
@@ -997,7 +1022,7 @@ class CudaEngine : public Engine {
   static constexpr uint32_t DENSE_LIST = 1u << 16;
   int merge_grid(uint32_t list_len) const {
     if (force_grid_ > 0) return force_grid_;
-    const uint64_t ctas = (static_cast<uint64_t>(list_len) + 255) / 256, maxg = static_cast<uint64_t>(n_sm_ - (srv_enabled_ ? 1 : 0)) * merge_ctas_per_sm_;  // one SM may hold the merge server
+    const uint64_t ctas = (static_cast<uint64_t>(list_len) + 255) / 256, maxg = static_cast<uint64_t>(std::max(1, n_sm_ - std::max(live_servers().load(), srv_enabled_ ? 1 : 0))) * merge_ctas_per_sm_;  // SMs held by merge servers are not ours
     return static_cast<int>(ctas < 1 ? 1 : (ctas < maxg ? ctas : maxg));
   }
 
@@ -1083,6 +1108,7 @@ class CudaEngine : public Engine {
     if (dbg_print_ && dbg_n_) {
       if (small_n_) std::fprintf(stderr, "[KTIME]\t of which %llu k_merge_small launches: probe+deltas %.1f us, fold+publish %.1f us | kernel (events) %.1f us\n", (unsigned long long)small_n_,
                                  1e3 * small_acc_[0] / small_n_, 1e3 * small_acc_[1] / small_n_, 1e3 * small_acc_[2] / small_n_);
+      std::fprintf(stderr, "[KTIME]\t decoding the records of all merges took the host %.1f ms\n", fetch_ms_);
       std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
                    (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
     }
@@ -1116,7 +1142,8 @@ class CudaEngine : public Engine {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evm0_ = nullptr, evm1_ = nullptr;
   EngineConfig cfg_{};
   Params P_{};
-  bool loaded_ = false;
+  bool loaded_ = false, fresh_ = false;
+  uint8_t keep_[256] = {};
   uint32_t n_words_ = 0;
   uint64_t n_slots_ = 0, n_live_ = 0, ids_cap_ = 0;
   int32_t* ids_ = nullptr;
@@ -1157,7 +1184,7 @@ class CudaEngine : public Engine {
   uint64_t vocab_hint_ = 32768;
   EngineStats es_{};
   uint64_t launches_ = 0, merge_seq_ = 0;
-  double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0;
+  double wait_ms_ = 0, launch_ms_ = 0, merge_ms_ = 0, fetch_ms_ = 0;
   int timing_every_ = 0;
   ull* dbg_ = nullptr;
   bool dbg_print_ = false;

@@ -92,6 +92,73 @@ __global__ void __launch_bounds__(256, 4) k_count(const int4* __restrict__ ids4,
     }
 }
 
+// Count pass of a FRESH corpus (every token is one byte): the pair space is at most 256 x 256, so each CTA aggregates into a
+// DIRECT-INDEXED shared-memory table over the dense codes of the bytes in use (K <= 111 distinct bytes: K^2 x 16 B <= 197 KB) --
+// no hashing, no probing, no CAS: per adjacent pair one LUT lookup per byte and four native 32-bit shared atomics (sum low half,
+// carry, occurrences, minimum position).  ncu on k_count showed the hashed table's instructions (84 per slot), not HBM, as the
+// limit.  One flush per CTA and used pair into the delta table at the end.
+struct ByteLut { uint8_t code[256]; };  // dense code of a byte value, 0xFF = not a countable symbol (unused, or the value unk symbols carry)
+__global__ void __launch_bounds__(256) k_count_dense(const int4* __restrict__ ids4, const uint4* __restrict__ wid4, uint32_t n4, const ull* __restrict__ wcnt, const ByteLut lut,
+                                                     uint32_t K, DeltaTable dt, DevCounters* ctr, uint64_t seq_base) {
+  extern __shared__ __align__(16) unsigned char dense_smem[];
+  uint32_t* lo = reinterpret_cast<uint32_t*>(dense_smem);
+  const uint32_t KK = K * K;
+  uint32_t *hi = lo + KK, *cnt = hi + KK, *mp = cnt + KK;
+  __shared__ uint8_t s_code[256];
+  __shared__ uint8_t s_byte[256];  // dense code -> byte value
+  s_code[threadIdx.x] = lut.code[threadIdx.x];
+  if (lut.code[threadIdx.x] != 0xFF) s_byte[lut.code[threadIdx.x]] = static_cast<uint8_t>(threadIdx.x);
+  for (uint32_t i = threadIdx.x; i < KK; i += blockDim.x) { lo[i] = 0u; hi[i] = 0u; cnt[i] = 0u; mp[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  const int32_t* ids = reinterpret_cast<const int32_t*>(ids4);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n4_ceil = (n4 + 31u) & ~31u, stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4_ceil; i0 += stride * CNT_UNROLL) {
+    int4 v[CNT_UNROLL];
+    uint4 w[CNT_UNROLL];
+    int32_t after[CNT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CNT_UNROLL; u++) {
+      const uint64_t i = static_cast<uint64_t>(i0) + static_cast<uint64_t>(u) * stride;
+      const bool in = i < n4;
+      v[u] = in ? __ldg(ids4 + i) : make_int4(DEAD, DEAD, DEAD, DEAD);
+      w[u] = in ? __ldg(wid4 + i) : make_uint4(0, 0, 0, 0);
+      after[u] = (lane == 31 && i + 1 < n4) ? __ldg(ids + 4 * (i + 1)) : DEAD;
+    }
+#pragma unroll
+    for (int u = 0; u < CNT_UNROLL; u++) {
+      const uint64_t i = static_cast<uint64_t>(i0) + static_cast<uint64_t>(u) * stride;
+      if (i >= n4_ceil) break;  // uniform per warp
+      int32_t nxt = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
+      if (lane == 31) nxt = after[u];
+      const int32_t sv[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nxt};
+      const uint32_t ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+      uint32_t cd[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) cd[k] = (static_cast<uint32_t>(sv[k]) < 256u) ? s_code[sv[k]] : 0xFFu;  // headers, padding and out-of-range unk codes are not symbols
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (cd[k] != 0xFFu && cd[k + 1] != 0xFFu) {  // bpe.cpp:201
+        const uint32_t e = cd[k] * K + cd[k + 1];
+        const ull c = wcnt[ws[k]];
+        const uint32_t c_lo = static_cast<uint32_t>(c), c_hi = static_cast<uint32_t>(c >> 32);
+        const uint32_t old = atomicAdd(&lo[e], c_lo);
+        const uint32_t up = c_hi + (old + c_lo < old ? 1u : 0u);
+        if (up) atomicAdd(&hi[e], up);
+        atomicAdd(&cnt[e], 1u);
+        const uint32_t pos = static_cast<uint32_t>(4ull * i + k);
+        if (pos < *reinterpret_cast<volatile uint32_t*>(&mp[e])) atomicMin(&mp[e], pos);  // positions grow along the grid-stride loop: rarely taken
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < KK; e += blockDim.x)
+    if (cnt[e]) {
+      const uint64_t key = fc_key(static_cast<int32_t>(s_byte[e / K]), static_cast<int32_t>(s_byte[e % K]));
+      const uint32_t ds = dt_add(dt, ctr, key, static_cast<int64_t>((static_cast<ull>(hi[e]) << 32) | lo[e]), seq_base | mp[e]);
+      if (ds != NONE32) atomicAdd(&dt.nocc[ds], cnt[e]);
+    }
+}
+
 // read-only probe of the pair table: the slot of `key`, or ~0 if it is absent
 __device__ __forceinline__ uint64_t pt_lookup(const PairTable& pt, uint64_t key) {
   uint64_t slot = mix64(key) & pt.mask;
