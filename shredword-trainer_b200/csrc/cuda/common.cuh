@@ -207,7 +207,7 @@ __device__ __forceinline__ uint64_t pt_find_or_claim(const PairTable& pt, DevCou
 
 // Finds `key` (inserting it if absent) and returns its slot; *old_freq = its frequency (0 for a new entry).
 // `first` is the already-loaded entry at the home slot (lets the caller issue several home loads back to back).
-// Only finalize_block calls this, with distinct keys per pass, so a claimed entry has exactly one writer.
+// Used for the merged pair's own entry (one thread per pass); the folds use pt_find_or_claim and batch the serial counter.
 __device__ __forceinline__ uint64_t pt_find_or_insert(const PairTable& pt, DevCounters* ctr, uint64_t key, ulonglong2 first, uint64_t* old_freq) {
   uint64_t slot = mix64(key) & pt.mask;
   ulonglong2 e = first;

@@ -585,6 +585,7 @@ class CudaEngine : public Engine {
       RC(alloc_dt(cap));
     }
     if (!pt_.ent) RC(alloc_pt(&pt_, 1ull << 20));
+    RC(ensure_scratch(2 * SMALL_MAX));  // the one-CTA kernel and the merge server never wait for scratch
     return 0;
   }
   int alloc_dt(uint64_t cap) {
@@ -858,7 +859,7 @@ class CudaEngine : public Engine {
       ma.dbg = timed ? dbg_ : nullptr;
       ma.D = dist_;
       if (small) {
-        const uint32_t nt = std::max<uint32_t>(64u, (list_len + 31u) & ~31u);  // one list entry per thread
+        const uint32_t nt = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (list_len + 31u) & ~31u));  // one list entry per thread, up to four beyond 1024
         k_merge_small<<<1, nt, sizeof(SmallStage), st_>>>(ma, small_slots_for(list_len));
         CK(cudaGetLastError());
       } else {

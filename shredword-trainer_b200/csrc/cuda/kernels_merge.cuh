@@ -26,16 +26,25 @@ struct MergeArgs {
 
 // One list entry: load everything the probe certainly or probably reads in one round trip (the token, its right neighbour, the
 // neighbour after that, the slot on its left), then probe.  The word's count travels in the list entry.
-__device__ __forceinline__ bool probe_entry(const MergeArgs& a, const PoolEnt e, lay::Occ* o, ull* c) {
+struct EntrySyms { int32_t v_p, v_b, v_r, v_m; };
+__device__ __forceinline__ EntrySyms load_entry(const MergeArgs& a, const PoolEnt e) {
   const int32_t* ids = a.ids;
   const uint32_t p = e.pos;
   const uint64_t pB = static_cast<uint64_t>(p) + a.lenA, pR = min(pB + a.lenB, a.ids_cap - 1);
-  const int32_t v_p = ids[p], v_b = ids[pB < a.ids_cap ? pB : a.ids_cap - 1], v_r = ids[pR], v_m = ids[p - 1];
-  if (v_p != a.A || v_b != a.B) return false;
+  EntrySyms y;
+  y.v_p = ids[p]; y.v_b = ids[pB < a.ids_cap ? pB : a.ids_cap - 1]; y.v_r = ids[pR]; y.v_m = ids[p - 1];
+  return y;
+}
+__device__ __forceinline__ bool probe_loaded(const MergeArgs& a, const PoolEnt e, const EntrySyms& y, lay::Occ* o, ull* c) {
+  if (y.v_p != a.A || y.v_b != a.B) return false;
+  const int32_t* ids = a.ids;
+  const uint32_t p = e.pos;
+  const uint64_t pB = static_cast<uint64_t>(p) + a.lenA, pR = min(pB + a.lenB, a.ids_cap - 1);
   *c = e.cnt != CNT_SAT ? static_cast<ull>(e.cnt) : a.wcnt[a.wid[p]];
-  auto ld = [&](uint64_t q) { return q == p ? v_p : q == pB ? v_b : q == pR ? v_r : q + 1 == p ? v_m : ids[q]; };
+  auto ld = [&](uint64_t q) { return q == p ? y.v_p : q == pB ? y.v_b : q == pR ? y.v_r : q + 1 == p ? y.v_m : ids[q]; };
   return lay::probe_occurrence(ld, p, a.A, a.B, a.lenA, a.lenB, a.N, a.P, o);
 }
+__device__ __forceinline__ bool probe_entry(const MergeArgs& a, const PoolEnt e, lay::Occ* o, ull* c) { return probe_loaded(a, e, load_entry(a, e), o, c); }
 
 // The per-merge kernel: one cooperative launch per merge, grid sized by the host from the length of the pair's occurrence list.
 // The reference scans every word for the pair (bpe.cpp:265-296); here the pair's occurrence list names the only slots that can
@@ -161,8 +170,7 @@ __global__ void __launch_bounds__(256) k_merge_virtual(const MergeArgs* argv, ui
 // Most merges of a run have occurrence lists of a few dozen to a few hundred entries, and for them a launch is pure latency:
 // ncu on such launches shows ~340 instructions per warp spread over ~10 000 cycles -- barriers waiting for the slowest warp,
 // instruction fetch, and a chain of dependent round trips (profiles/r02).  k_merge_small therefore runs the three phases in ONE
-// CTA sized to the list (one entry per thread), with the delta table, the touched-key list and the per-occurrence scratch in
-// SHARED memory and as few block barriers and dependent round trips as the data flow allows:
+// CTA sized to the list (up to four entries per thread), with the delta table and the touched-key list in SHARED memory and as few block barriers and dependent round trips as the data flow allows:
 //   phase 1  list entry -> symbols (one batch of loads) -> the occurrence's four keys go into the shared table together (loads,
 //            claims and adds of all four issued before the first result is used); the first thread to see a key prefetches the
 //            key's pair-table sector into L2
@@ -173,20 +181,19 @@ __global__ void __launch_bounds__(256) k_merge_virtual(const MergeArgs* argv, ui
 // Sequence numbers are 32 bits here (slot * 4 + delta slot), so the host uses it only below 2^30 slots, on one GPU, for lists
 // of at most SMALL_MAX entries.  If the shared table cannot place a key the kernel publishes ERR_RETRY before it has changed
 // anything in global memory, and the host runs the general kernel instead.
-constexpr uint32_t SMALL_MAX = 1024, SMALL_SLOTS_MAX = 4096, SMALL_PROBES = 32;
+constexpr uint32_t SMALL_MAX = 4096, SMALL_PER_THREAD = 4, SMALL_SLOTS_MAX = 4096, SMALL_PROBES = 32;  // up to 1024 threads x 4 list entries
 constexpr uint32_t ERR_RETRY = 0x40000000u;
 struct SmallStage {
   ull key[SMALL_SLOTS_MAX];                                   // dt.empty = free; the launch uses the first `slots` (a power of two >= 4 x list length)
   uint32_t lo[SMALL_SLOTS_MAX], hi[SMALL_SLOTS_MAX];          // net delta as two 32-bit halves (shared adds are native for 32 bits only); after the fold: list base
   uint32_t seq[SMALL_SLOTS_MAX], nocc[SMALL_SLOTS_MAX];
   uint32_t used[SMALL_SLOTS_MAX];                             // dense list of claimed slots
-  uint4 occ_a[SMALL_MAX]; uint4 occ_b[SMALL_MAX];             // as OccScratch, slots being SHARED-table slots
   ull pt_after, pool_after;                                   // counters as this pass leaves them (0: untouched)
   uint32_t n_keys, n_occ, n_recs, overflow;
 };
 __host__ __device__ inline uint32_t small_slots_for(uint32_t list_len) {
   uint32_t n = 128;
-  while (n < 4u * list_len && n < SMALL_SLOTS_MAX) n <<= 1;
+  while (n < 4u * list_len && n < SMALL_SLOTS_MAX) n <<= 1;  // (longer lists: the keys of a merge are far fewer than 4 per entry; ERR_RETRY otherwise)
   return n;
 }
 __device__ __forceinline__ void small_apply(SmallStage& s, uint32_t slot, int64_t delta, uint32_t seq, bool want_rank, uint32_t* rank_out) {
@@ -234,13 +241,22 @@ __device__ __forceinline__ bool small_merge_body(SmallStage& s, const MergeArgs&
   const ListRef lr = a.pt.lists[a.serial];  // in flight while the tables are cleared
   if (t == nt - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(&a.pt.ent[mix64(fc_key(a.A, a.B)) & a.pt.mask]));  // phase 2 zeroes the merged pair's frequency there
   if (!PRECLEARED) { small_clear(s, slots, empty); __syncthreads(); }
-  // ---- phase 1: one list entry per thread
-  if (t < lr.len && lr.len <= nt) {
-    const PoolEnt e = a.pool[lr.off + t];
-    ull c = 0;
-    lay::Occ o;
-    if (probe_entry(a, e, &o, &c)) {
-      const uint32_t p = e.pos, seq = p * 4u;
+  // ---- phase 1: up to SMALL_PER_THREAD list entries per thread; entries first, then all their symbols, then the probes
+  if (lr.len <= nt * SMALL_PER_THREAD) {
+    PoolEnt e[SMALL_PER_THREAD];
+    EntrySyms y[SMALL_PER_THREAD];
+#pragma unroll
+    for (uint32_t j = 0; j < SMALL_PER_THREAD; j++) { const uint32_t i = t + j * nt; if (i < lr.len) e[j] = a.pool[lr.off + i]; }
+#pragma unroll
+    for (uint32_t j = 0; j < SMALL_PER_THREAD; j++) { const uint32_t i = t + j * nt; if (i < lr.len) y[j] = load_entry(a, e[j]); }
+#pragma unroll
+    for (uint32_t j = 0; j < SMALL_PER_THREAD; j++) {
+      const uint32_t i = t + j * nt;
+      if (i >= lr.len) break;
+      ull c = 0;
+      lay::Occ o;
+      if (!probe_loaded(a, e[j], y[j], &o, &c)) continue;
+      const uint32_t p = e[j].pos, seq = p * 4u;
       const int64_t cc = static_cast<int64_t>(c);
       const uint64_t key[4] = {fc_key(o.lid, a.A), fc_key(o.lid, a.N), fc_key(a.B, o.rid), fc_key(a.N, o.rid)};  // bpe.cpp:274-290
       const bool has[4] = {o.has_l, o.has_l, o.has_r, o.has_r};
@@ -249,26 +265,28 @@ __device__ __forceinline__ bool small_merge_body(SmallStage& s, const MergeArgs&
       ull cur[4];
       // the four keys together: home slots, claims, then every add before any result is used
 #pragma unroll
-      for (int j = 0; j < 4; j++) { slot[j] = static_cast<uint32_t>(mix64(key[j])) & mask; cur[j] = has[j] ? s.key[slot[j]] : 0ull; }
+      for (int q = 0; q < 4; q++) { slot[q] = static_cast<uint32_t>(mix64(key[q])) & mask; cur[q] = has[q] ? s.key[slot[q]] : 0ull; }
 #pragma unroll
-      for (int j = 0; j < 4; j++) if (has[j] && cur[j] == empty) {
-        const ull prev = atomicCAS(&s.key[slot[j]], empty, static_cast<ull>(key[j]));
-        if (prev == empty) { small_claimed(s, a, slot[j], key[j]); cur[j] = key[j]; } else cur[j] = prev;
+      for (int q = 0; q < 4; q++) if (has[q] && cur[q] == empty) {
+        const ull prev = atomicCAS(&s.key[slot[q]], empty, static_cast<ull>(key[q]));
+        if (prev == empty) { small_claimed(s, a, slot[q], key[q]); cur[q] = key[q]; } else cur[q] = prev;
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) if (has[j] && cur[j] == key[j]) small_apply(s, slot[j], (j & 1) ? cc : -cc, seq + static_cast<uint32_t>(j), list[j], &rank[j]);
+      for (int q = 0; q < 4; q++) if (has[q] && cur[q] == key[q]) small_apply(s, slot[q], (q & 1) ? cc : -cc, seq + static_cast<uint32_t>(q), list[q], &rank[q]);
       bool fit = true;
 #pragma unroll
-      for (int j = 0; j < 4; j++) if (has[j] && cur[j] != key[j]) fit &= small_add_probe(s, a, mask, key[j], (j & 1) ? cc : -cc, seq + static_cast<uint32_t>(j), list[j], &slot[j], &rank[j]);
+      for (int q = 0; q < 4; q++) if (has[q] && cur[q] != key[q]) fit &= small_add_probe(s, a, mask, key[q], (q & 1) ? cc : -cc, seq + static_cast<uint32_t>(q), list[q], &slot[q], &rank[q]);
       if (!fit) s.overflow = 1u;
       const uint32_t idx = atomicAdd(&s.n_occ, 1u);
-      s.occ_a[idx] = make_uint4(p, o.pl, list[1] ? slot[1] : NONE32, rank[1]);
-      s.occ_b[idx] = make_uint4(list[3] ? slot[3] : NONE32, rank[3], c < CNT_SAT ? static_cast<uint32_t>(c) : CNT_SAT, 0u);
+      if (idx < a.sc.cap) {
+        a.sc.a[idx] = make_uint4(p, o.pl, list[1] ? slot[1] : NONE32, rank[1]);
+        a.sc.b[idx] = make_uint4(list[3] ? slot[3] : NONE32, rank[3], c < CNT_SAT ? static_cast<uint32_t>(c) : CNT_SAT, 0u);
+      } else s.overflow = 1u;
     }
   }
   __syncthreads();
   if (t == 0 && a.dbg) a.dbg[1] = gtime();
-  if (s.overflow || lr.len > nt) {  // nothing in global memory has been touched: hand the merge to the general kernel
+  if (s.overflow || lr.len > nt * SMALL_PER_THREAD || s.n_keys > SMALL_SLOTS_MAX) {  // nothing but scratch has been written: hand the merge to the general kernel
     if (t == 0) wire_ctrl(a.ctrl, a.tag, 0u, ERR_RETRY, lr.len, 0u, 0ull, 0u, 0ull, 0ull);
     return false;
   }
@@ -380,9 +398,9 @@ __device__ __forceinline__ bool small_merge_body(SmallStage& s, const MergeArgs&
   // ---- phase 3: rewrite the occurrences, fill the new pairs' lists (the host is already replaying its heap)
   int32_t* idsw = a.ids;
   auto st = [idsw](uint64_t q, int32_t v2) { idsw[q] = v2; };
-  if (t < n_occ) {
-    const uint4 x = s.occ_a[t];
-    const uint4 y = s.occ_b[t];
+  for (uint32_t i = t; i < n_occ; i += nt) {
+    const uint4 x = a.sc.a[i];
+    const uint4 y = a.sc.b[i];
     const ull b1 = x.z != NONE32 ? ((static_cast<ull>(s.hi[x.z]) << 32) | s.lo[x.z]) : NO_LIST, b2 = y.x != NONE32 ? ((static_cast<ull>(s.hi[y.x]) << 32) | s.lo[y.x]) : NO_LIST;
     lay::rewrite_occurrence(st, x.x, a.lenA, a.lenB, a.N);
     PoolEnt ne; ne.cnt = y.z;
