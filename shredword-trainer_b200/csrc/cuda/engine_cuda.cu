@@ -375,7 +375,7 @@ class CudaEngine : public Engine {
   void free_wt(WordTable& wt) { cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_); }
 
   // pinned staging ring shared by all trainers of the process (cudaHostAlloc is slow, so it is done once)
-  static constexpr int STAGE_BUFS = 8;
+  static constexpr int STAGE_BUFS = 12;
   static constexpr size_t STAGE_BYTES = 16u << 20;
   struct StageRing { uint8_t* buf[STAGE_BUFS] = {}; std::mutex mu; };
   static StageRing& stage_ring() { static StageRing r; return r; }

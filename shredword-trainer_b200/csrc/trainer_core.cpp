@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 // NVTX ranges per phase: only in the product build (build.py defines SHRED_NVTX; nvtx3 is header-only and
 // costs a null-pointer check per call unless a profiler has injected itself)
@@ -173,8 +174,13 @@ int TrainerCore::finish_load(size_t n, double t0) {
   abi_->corpus.words = static_cast<Symbol**>(std::malloc((N ? N : 1) * sizeof(Symbol*)));
   abi_->corpus.word_counts = static_cast<uint64_t*>(std::malloc((N ? N : 1) * sizeof(uint64_t)));
   if (!abi_->corpus.words || !abi_->corpus.word_counts) return -1;
-  for (size_t i = 0; i < N; i++) abi_->corpus.words[i] = &placeholder_;
-  if (N && eng_->word_counts(abi_->corpus.word_counts) != 0) return -1;
+  // two 8-byte-per-word host arrays (131 MB each at 10 GB): fill one on a helper thread while the counts come back from the device
+  Symbol** words = abi_->corpus.words;
+  Symbol* ph = &placeholder_;
+  std::thread filler([words, ph, N]() { for (size_t i = 0; i < N; i++) words[i] = ph; });
+  const int wrc = N ? eng_->word_counts(abi_->corpus.word_counts) : 0;
+  filler.join();
+  if (wrc != 0) return -1;
   // bpe.cpp:183 re-initialises the pair table; the heap is left alone (it is reset by bpe_init)
   version_.clear(); phantom_.clear(); ver_.clear();
   load_wall_ms_ = now_ms() - t0;
