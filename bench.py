@@ -430,7 +430,7 @@ def main():
                         "memory (tmpfs), both output files written; max over ranks",
                 "load_s_per_step": phase[0], "train_s_per_step": phase[1], "save_s_per_step": phase[2],
                 "cold_first_step": {"load_s": cold["load_s"], "train_s": cold["train_s"], "save_s": cold["save_s"],
-                                    "what": "first step of the process (warm-up 0): first device allocations, pinning of the staging ring, lazy module load included"} if cold else None,
+                                    "what": "first step of the process (warm-up 0): allocator pool growth, pinned staging ring, lazy module load included"} if cold else None,
                 "load_buffer_variant": side_buffer},
         "gpu_launches": int(S("kernel_launches")),
         "roofline": {"bound": "hbm", "kernel": "k_merge_small / k_merge (one launch per merge: probe the pair's occurrence list + count deltas | fold + publish | rewrite + new lists)",

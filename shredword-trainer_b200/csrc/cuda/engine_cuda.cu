@@ -119,66 +119,6 @@ struct VirtualCluster {
   }
 };
 
-// Large device buffers (corpus text, symbols, word indices, occurrence lists, tables) come from plain cudaMalloc -- 1.5 ms for
-// 10 GB and 4 ms for 40 GB on this driver, where the first cudaMallocAsync of that size has to grow the stream-ordered pool
-// through the virtual-memory API (57 ms / 929 ms measured): the first bpe_load_corpus of a process paid 0.5 s for that at 10 GB.
-// cudaFree would synchronise the whole device (and wait for any resident merge server), so freed blocks are kept here instead,
-// each with an event recorded on the stream that last used it, and handed out again to the next request of a similar size;
-// they go back to the driver only when an allocation fails.  Small buffers stay with the stream-ordered pool.
-class DeviceArena {
- public:
-  static constexpr size_t BIG = 32ull << 20;
-  static DeviceArena& get(int dev) { static DeviceArena a[64]; return a[dev & 63]; }
-  int alloc(void** out, size_t bytes, cudaStream_t st) {
-    std::lock_guard<std::mutex> g(mu_);
-    size_t best = free_.size();
-    for (size_t i = 0; i < free_.size(); i++)
-      if (free_[i].bytes >= bytes && free_[i].bytes <= bytes + bytes / 2 && (best == free_.size() || free_[i].bytes < free_[best].bytes)) best = i;
-    Block b;
-    if (best != free_.size()) {
-      b = free_[best];
-      free_.erase(free_.begin() + static_cast<std::ptrdiff_t>(best));
-      if (cudaStreamWaitEvent(st, b.ev, 0) != cudaSuccess) return -1;  // its previous user (any stream, any trainer) has finished with it
-    } else {
-      b.bytes = bytes;
-      if (cudaMalloc(&b.p, bytes) != cudaSuccess) {
-        cudaGetLastError();
-        trim_locked();
-        cudaMemPool_t pool;
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-        if (cudaMalloc(&b.p, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
-      }
-      if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) { cudaFree(b.p); return -1; }
-    }
-    live_.push_back(b);
-    *out = b.p;
-    return 0;
-  }
-  // true if the pointer was ours
-  bool release(void* p, cudaStream_t st) {
-    std::lock_guard<std::mutex> g(mu_);
-    for (size_t i = 0; i < live_.size(); i++) if (live_[i].p == p) {
-      Block b = live_[i];
-      live_[i] = live_.back(); live_.pop_back();
-      cudaEventRecord(b.ev, st);
-      free_.push_back(b);
-      return true;
-    }
-    return false;
-  }
-  void trim() { std::lock_guard<std::mutex> g(mu_); trim_locked(); }
-
- private:
-  struct Block { void* p = nullptr; size_t bytes = 0; cudaEvent_t ev = nullptr; };
-  void trim_locked() {
-    for (Block& b : free_) { cudaEventSynchronize(b.ev); cudaFree(b.p); cudaEventDestroy(b.ev); }
-    free_.clear();
-  }
-  std::mutex mu_;
-  std::vector<Block> live_, free_;
-};
-
 class CudaEngine : public Engine {
  public:
   CudaEngine(int dev, const cudaDeviceProp& prop) : dev_(dev), n_sm_(prop.multiProcessorCount > 0 ? prop.multiProcessorCount : N_SM_FALLBACK) {
@@ -193,7 +133,7 @@ class CudaEngine : public Engine {
     CK(cudaHostAlloc(&cp, sizeof(Ctrl), cudaHostAllocMapped));
     std::memset(cp, 0, sizeof(Ctrl));
     ctrl_ = static_cast<Ctrl*>(cp);
-    CK(dalloc(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters)));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters), st_));
     CK(cudaMemset(ctr_, 0, sizeof(DevCounters)));
     CK(cudaEventCreate(&ev0_));
     CK(cudaEventCreate(&ev1_));
@@ -343,18 +283,6 @@ class CudaEngine : public Engine {
 
   // bpe_load_corpus(path): the file goes to HBM through a ring of pinned staging buffers, one reader thread per buffer
   // (pread from the page cache) while the previous chunks are already in flight over PCIe.
-  // device memory: large blocks from the arena (plain cudaMalloc, cached), small ones from the stream-ordered pool
-  cudaError_t dalloc(void** p, size_t bytes) {
-    if (bytes >= DeviceArena::BIG) return DeviceArena::get(dev_).alloc(p, bytes, st_) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
-    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st_);
-    if (e != cudaSuccess) { cudaGetLastError(); DeviceArena::get(dev_).trim(); e = cudaMallocAsync(p, bytes ? bytes : 1, st_); }  // the arena's cache may be what is in the way
-    return e;
-  }
-  void dfree(void* p) {
-    if (!p) return;
-    if (!DeviceArena::get(dev_).release(p, st_)) cudaFreeAsync(p, st_);
-  }
-
   int load_file(int fd, size_t n, const EngineConfig& cfg, LoadInfo* info) override { return load_impl(nullptr, fd, n, cfg, info); }
 
   int load_impl(const uint8_t* text, int fd, size_t n, const EngineConfig& cfg, LoadInfo* info) {
@@ -372,7 +300,7 @@ class CudaEngine : public Engine {
     const uint64_t padded = ((n + 15) & ~15ull) + 64;
     uint8_t* d_text = nullptr;
     const double ta = now_ms();
-    CK(dalloc(reinterpret_cast<void**>(&d_text), padded));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_text), padded, st_));
     PreTok pre;
     double t0 = now_ms();
     if (n && text) CK(cudaMemcpyAsync(d_text, text, n, cudaMemcpyHostToDevice, st_));
@@ -385,8 +313,33 @@ class CudaEngine : public Engine {
       CK(cudaMemsetAsync(ctr_, 0, sizeof(DevCounters), st_));
       bar_count_ = 0;
       pre.valid = true;
+      // First load of a process: the stream-ordered pool is still small and every later allocation of the ingest (symbols, word
+      // indices, occurrence lists: ~0.6 B per corpus byte) would grow it on the critical path (0.78 s at 10 GB).  Grow it now, on a
+      // helper thread and stream, while the file is on its way over PCIe.
+      std::thread warm;
+      {
+        cudaMemPool_t pool; uint64_t reserved = 0, used = 0; size_t free_b = 0, total_b = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+          uint64_t want = n - n / 4, idle = reserved > used ? reserved - used : 0;
+          if (want > free_b / 3) want = free_b / 3;
+          if (want > idle + (256ull << 20)) {
+            const uint64_t grow = want - idle;
+            const int dev = dev_;
+            warm = std::thread([grow, dev]() {
+              cudaSetDevice(dev);
+              cudaStream_t sa; void* p = nullptr;
+              if (cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking) != cudaSuccess) return;
+              if (cudaMallocAsync(&p, grow, sa) == cudaSuccess) cudaFreeAsync(p, sa);
+              cudaStreamSynchronize(sa);
+              cudaStreamDestroy(sa);
+            });
+          }
+        }
+      }
       const int src = stream_file(fd, n, d_text, &pre);
-      if (src != 0) { free_wt(pre.wt); dfree(d_text); return -1; }
+      if (warm.joinable()) warm.join();
+      if (src != 0) { free_wt(pre.wt); cudaFreeAsync(d_text, st_); return -1; }
     } else {
       CK(cudaMemsetAsync(d_text + n, ' ', padded - n, st_));
     }
@@ -397,7 +350,7 @@ class CudaEngine : public Engine {
     CK(cudaEventRecord(ev0_, st_));
     const double ti = now_ms();
     int rc = ingest(d_text, n, info, pre);
-    dfree(d_text);
+    cudaFreeAsync(d_text, st_);
     if (rc != 0) return rc;
     CK(cudaEventRecord(ev1_, st_));
     CK(cudaStreamSynchronize(st_));
@@ -412,14 +365,14 @@ class CudaEngine : public Engine {
   struct PreTok { WordTable wt{}; uint64_t cap = 0; uint32_t seed = 0; bool valid = false; };
   static uint64_t wt_cap_for(uint64_t n) { uint64_t cap = next_pow2(n / 64 + 1); return cap < (1u << 16) ? (1u << 16) : cap; }  // grown 4x and redone if more than half fills up
   int alloc_wt(WordTable* wt, uint64_t cap) {
-    CK(dalloc(reinterpret_cast<void**>(&wt->tag), cap * 8)); CK(dalloc(reinterpret_cast<void**>(&wt->first), cap * 8));
-    CK(dalloc(reinterpret_cast<void**>(&wt->count), cap * 8)); CK(dalloc(reinterpret_cast<void**>(&wt->len), cap * 4));
-    CK(dalloc(reinterpret_cast<void**>(&wt->bucket), cap * 4));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->tag), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->first), cap * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->count), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->len), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wt->bucket), cap * 4, st_));
     wt->cap = cap; wt->mask = cap - 1;
     CK(cudaMemsetAsync(wt->tag, 0, cap * 8, st_)); CK(cudaMemsetAsync(wt->first, 0xFF, cap * 8, st_)); CK(cudaMemsetAsync(wt->count, 0, cap * 8, st_));
     return 0;
   }
-  void free_wt(WordTable& wt) { dfree(wt.tag); dfree(wt.first); dfree(wt.count); dfree(wt.len); dfree(wt.bucket); }
+  void free_wt(WordTable& wt) { cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_); }
 
   // pinned staging ring shared by all trainers of the process (cudaHostAlloc is slow, so it is done once)
   static constexpr int STAGE_BUFS = 12;
@@ -516,12 +469,12 @@ class CudaEngine : public Engine {
       CK(cudaStreamSynchronize(st_));
       CK(cudaGetLastError());
       if (c.err & ERR_HAS_NUL) {
-        dfree(wt.tag); dfree(wt.first); dfree(wt.count); dfree(wt.len); dfree(wt.bucket);
+        cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_);
         return 1;
       }
       const bool too_full = static_cast<uint64_t>(c.n_unique) * 2 > cap;
       if ((c.err & (ERR_WT_FULL | ERR_WT_COLLISION)) || too_full) {
-        dfree(wt.tag); dfree(wt.first); dfree(wt.count); dfree(wt.len); dfree(wt.bucket);
+        cudaFreeAsync(wt.tag, st_); cudaFreeAsync(wt.first, st_); cudaFreeAsync(wt.count, st_); cudaFreeAsync(wt.len, st_); cudaFreeAsync(wt.bucket, st_);
         if ((c.err & ERR_WT_FULL) || too_full) cap *= 4;
         if (c.err & ERR_WT_COLLISION) seed = seed * 2654435761u + 12345u;
         continue;
@@ -539,22 +492,22 @@ class CudaEngine : public Engine {
     uint8_t* d_keep = nullptr;
     uint32_t* wlen = nullptr;  // word lengths: only needed until the offsets exist
     const uint64_t Na = N ? N : 1;
-    CK(dalloc(reinterpret_cast<void**>(&u_slot), Na * 4)); CK(dalloc(reinterpret_cast<void**>(&tmp_slot), Na * 4));
-    CK(dalloc(reinterpret_cast<void**>(&order_slot), Na * 4)); CK(dalloc(reinterpret_cast<void**>(&tmp_first), Na * 8));
-    CK(dalloc(reinterpret_cast<void**>(&len1), Na * 8));
-    CK(dalloc(reinterpret_cast<void**>(&u_n), 4)); CK(dalloc(reinterpret_cast<void**>(&bcnt), 4096 * 4));
-    CK(dalloc(reinterpret_cast<void**>(&bstart), 4097 * 4)); CK(dalloc(reinterpret_cast<void**>(&cursor), 4096 * 4));
-    CK(dalloc(reinterpret_cast<void**>(&d_hist), 256 * 8)); CK(dalloc(reinterpret_cast<void**>(&d_keep), 256));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&u_slot), Na * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&tmp_slot), Na * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&order_slot), Na * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&tmp_first), Na * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&len1), Na * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&u_n), 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&bcnt), 4096 * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&bstart), 4097 * 4, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&cursor), 4096 * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_hist), 256 * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&d_keep), 256, st_));
     const uint32_t nb_scan = static_cast<uint32_t>((Na + SCAN_TILE - 1) / SCAN_TILE);
-    CK(dalloc(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sums), (static_cast<uint64_t>(nb_scan) + 1) * 8, st_));
     auto free_tmp = [&]() {
-      dfree(u_slot); dfree(tmp_slot); dfree(order_slot); dfree(tmp_first); dfree(len1); dfree(u_n); dfree(bcnt);
-      dfree(bstart); dfree(cursor); dfree(d_hist); dfree(d_keep); dfree(sums); dfree(wlen);
+      cudaFreeAsync(u_slot, st_); cudaFreeAsync(tmp_slot, st_); cudaFreeAsync(order_slot, st_); cudaFreeAsync(tmp_first, st_); cudaFreeAsync(len1, st_); cudaFreeAsync(u_n, st_); cudaFreeAsync(bcnt, st_);
+      cudaFreeAsync(bstart, st_); cudaFreeAsync(cursor, st_); cudaFreeAsync(d_hist, st_); cudaFreeAsync(d_keep, st_); cudaFreeAsync(sums, st_); cudaFreeAsync(wlen, st_);
     };
     CK(cudaMemsetAsync(u_n, 0, 4, st_)); CK(cudaMemsetAsync(bcnt, 0, 4096 * 4, st_)); CK(cudaMemsetAsync(cursor, 0, 4096 * 4, st_));
     CK(cudaMemsetAsync(d_hist, 0, 256 * 8, st_));
-    CK(dalloc(reinterpret_cast<void**>(&wcnt_), Na * 8)); CK(dalloc(reinterpret_cast<void**>(&wlen), Na * 4));
-    CK(dalloc(reinterpret_cast<void**>(&woff_), (Na + 1) * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wcnt_), Na * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wlen), Na * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&woff_), (Na + 1) * 8, st_));
     ull S1 = 0;  // total slots = symbols + headers
     if (N) {
       k_collect<<<grid_for(cap, 256), 256, 0, st_>>>(wt, u_slot, u_n, bcnt);
@@ -592,12 +545,12 @@ class CudaEngine : public Engine {
       S1 = hoff[hi] - base_off;
       ull *wc = nullptr, *wo = nullptr;
       const uint64_t nl = n_local ? n_local : 1;
-      CK(dalloc(reinterpret_cast<void**>(&wc), nl * 8)); CK(dalloc(reinterpret_cast<void**>(&wo), (nl + 1) * 8));
+      CK(cudaMallocAsync(reinterpret_cast<void**>(&wc), nl * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&wo), (nl + 1) * 8, st_));
       if (n_local) {
         CK(cudaMemcpyAsync(wc, wcnt_ + lo, static_cast<uint64_t>(n_local) * 8, cudaMemcpyDeviceToDevice, st_));
         k_rebase<<<grid_for(n_local, 256), 256, 0, st_>>>(woff_ + lo, n_local, base_off, wo); launches_++;
       }
-      dfree(wcnt_); dfree(woff_);
+      cudaFreeAsync(wcnt_, st_); cudaFreeAsync(woff_, st_);
       wcnt_ = wc; woff_ = wo;
       es_.d2h_bytes += static_cast<uint64_t>(N) * 16;
     }
@@ -605,12 +558,12 @@ class CudaEngine : public Engine {
     n_slots_ = S1; n_live_ = S1;
     if (S1 + 64 >= (1ull << 32) || N >= lay::LOW30) { free_tmp(); free_wt(); std::fprintf(stderr, "[ERROR]\t corpus needs more than 2^32 symbol slots or 2^30 words on one GPU\n"); return -1; }
     ids_cap_ = ((S1 + 8 + 1023) / 1024) * 1024;
-    CK(dalloc(reinterpret_cast<void**>(&ids_), ids_cap_ * 4));
-    CK(dalloc(reinterpret_cast<void**>(&wid_), ids_cap_ * 4));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&ids_), ids_cap_ * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&wid_), ids_cap_ * 4, st_));
     CK(cudaMemsetAsync(wid_, 0, ids_cap_ * 4, st_));
     // occurrence lists: one entry per adjacent pair of the fresh corpus (< S1) + two per rewritten occurrence (< S1 - words)
     pool_cap_ = S1 + 2 * (S1 - n_local) + 1024;
-    CK(dalloc(reinterpret_cast<void**>(&pool_), pool_cap_ * sizeof(PoolEnt)));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pool_), pool_cap_ * sizeof(PoolEnt), st_));
     CK(cudaMemcpyAsync(d_keep, info->keep, 256, cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(woff_ + n_local, &S1, 8, cudaMemcpyHostToDevice, st_));
     if (n_local) { k_symbolize<<<grid_for(n_local, 256), 256, 0, st_>>>(d_text, wt, order_slot + lo, n_local, woff_, d_keep, P_.unk_code, ids_, wid_); launches_++; es_.ingest_launches++; }
@@ -638,13 +591,13 @@ class CudaEngine : public Engine {
   }
   int alloc_dt(uint64_t cap) {
     if (dt_.keys) {
-      dfree(dt_.keys); dfree(dt_.delta); dfree(dt_.seq); dfree(dt_.nocc); dfree(dt_.base);
-      dfree(dt_.list); dfree(dt_.klist); dt_.keys = nullptr;
+      cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.nocc, st_); cudaFreeAsync(dt_.base, st_);
+      cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_); dt_.keys = nullptr;
     }
-    CK(dalloc(reinterpret_cast<void**>(&dt_.keys), cap * 8)); CK(dalloc(reinterpret_cast<void**>(&dt_.delta), cap * 8));
-    CK(dalloc(reinterpret_cast<void**>(&dt_.seq), cap * 8)); CK(dalloc(reinterpret_cast<void**>(&dt_.nocc), cap * 4));
-    CK(dalloc(reinterpret_cast<void**>(&dt_.base), cap * 8)); CK(dalloc(reinterpret_cast<void**>(&dt_.list), cap * 4));
-    CK(dalloc(reinterpret_cast<void**>(&dt_.klist), cap * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.keys), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.delta), cap * 8, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.seq), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.nocc), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.base), cap * 8, st_)); CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.list), cap * 4, st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&dt_.klist), cap * 8, st_));
     dt_.cap = static_cast<uint32_t>(cap); dt_.mask = cap - 1;
     // a key value no pair can produce: high word >= 2^31 that is neither all-ones nor unk_id
     uint32_t hi = 0x80000000u; if (static_cast<uint32_t>(cfg_.unk_id) == hi) hi = 0x80000001u;
@@ -663,10 +616,10 @@ class CudaEngine : public Engine {
     return 0;
   }
   int alloc_pt(PairTable* pt, uint64_t cap) {
-    CK(dalloc(reinterpret_cast<void**>(&pt->ent), cap * sizeof(PairEnt)));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->ent), cap * sizeof(PairEnt), st_));
     pt->cap = cap; pt->mask = cap - 1;
     pt->lists_cap = cap / 2 + 4096;  // the table stays at most half full, serials are dense
-    CK(dalloc(reinterpret_cast<void**>(&pt->lists), pt->lists_cap * sizeof(ListRef)));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&pt->lists), pt->lists_cap * sizeof(ListRef), st_));
     CK(cudaMemsetAsync(pt->ent, 0xFF, cap * sizeof(PairEnt), st_));  // key = EMPTY; freq is written when the entry is claimed
     CK(cudaMemsetAsync(pt->lists, 0, pt->lists_cap * sizeof(ListRef), st_));  // len 0 = the pair has no list
     return 0;
@@ -679,7 +632,7 @@ class CudaEngine : public Engine {
     k_rehash<<<grid_for(pt_.cap, 256), 256, 0, st_>>>(pt_, nt, ctr_); launches_++;
     CK(cudaMemcpyAsync(nt.lists, pt_.lists, pt_.lists_cap * sizeof(ListRef), cudaMemcpyDeviceToDevice, st_));
     CK(cudaStreamSynchronize(st_));
-    dfree(pt_.ent); dfree(pt_.lists);
+    cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.lists, st_);
     pt_ = nt;
     return 0;
   }
@@ -688,9 +641,9 @@ class CudaEngine : public Engine {
     uint64_t cap = sc_.cap ? sc_.cap : (1u << 16);
     while (cap < n_entries) cap *= 2;
     if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
-    if (sc_.a) { dfree(sc_.a); dfree(sc_.b); }
-    CK(dalloc(reinterpret_cast<void**>(&sc_.a), cap * sizeof(uint4)));
-    CK(dalloc(reinterpret_cast<void**>(&sc_.b), cap * sizeof(uint4)));
+    if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.a), cap * sizeof(uint4), st_));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&sc_.b), cap * sizeof(uint4), st_));
     sc_.cap = static_cast<uint32_t>(cap);
     return 0;
   }
@@ -975,11 +928,11 @@ class CudaEngine : public Engine {
     RC(srv_stop());
     if (!loaded_ || (!n_words_ && world_ == 1) || !T) return 0;
     ull* d = nullptr;
-    CK(dalloc(reinterpret_cast<void**>(&d), T * 8));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d), T * 8, st_));
     CK(cudaMemsetAsync(d, 0, T * 8, st_));
     if (n_words_) { k_token_freq<<<grid_for(n_words_, 256), 256, 0, st_>>>(ids_, woff_, wcnt_, n_words_, P_, d, T); launches_++; }
     if (world_ > 1) {
-      if (T > INBOX_ENTRIES * 3) { dfree(d); std::fprintf(stderr, "[ERROR]\t vocabulary too large for the exchange buffer\n"); return -1; }
+      if (T > INBOX_ENTRIES * 3) { cudaFreeAsync(d, st_); std::fprintf(stderr, "[ERROR]\t vocabulary too large for the exchange buffer\n"); return -1; }
       const int grid = virtual_ ? VirtualCluster::GRID_PER_RANK : n_sm_ * 2;
       SumArgs sa;
       sa.vals = d; sa.T = T; sa.ctr = ctr_; sa.D = next_exchange(); sa.bar_base = bar_count_;
@@ -993,7 +946,7 @@ class CudaEngine : public Engine {
     }
     CK(cudaMemcpyAsync(freq, d, T * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
-    dfree(d);
+    cudaFreeAsync(d, st_);
     es_.d2h_bytes += T * 8;
     return 0;
   }
@@ -1142,11 +1095,11 @@ class CudaEngine : public Engine {
   }
 
   void release_corpus() {
-    if (ids_) dfree(ids_); ids_ = nullptr;
-    if (wid_) dfree(wid_); wid_ = nullptr;
-    if (woff_) dfree(woff_); woff_ = nullptr;
-    if (wcnt_) dfree(wcnt_); wcnt_ = nullptr;
-    if (pool_) dfree(pool_); pool_ = nullptr;
+    if (ids_) cudaFreeAsync(ids_, st_); ids_ = nullptr;
+    if (wid_) cudaFreeAsync(wid_, st_); wid_ = nullptr;
+    if (woff_) cudaFreeAsync(woff_, st_); woff_ = nullptr;
+    if (wcnt_) cudaFreeAsync(wcnt_, st_); wcnt_ = nullptr;
+    if (pool_) cudaFreeAsync(pool_, st_); pool_ = nullptr;
     pool_cap_ = 0;
     n_words_ = 0; n_slots_ = n_live_ = 0; loaded_ = false; pt_n_ = 0;
   }
@@ -1162,14 +1115,14 @@ class CudaEngine : public Engine {
     }
     release_corpus();
     if (dt_.keys) {
-      dfree(dt_.keys); dfree(dt_.delta); dfree(dt_.seq); dfree(dt_.nocc); dfree(dt_.base);
-      dfree(dt_.list); dfree(dt_.klist);
+      cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.nocc, st_); cudaFreeAsync(dt_.base, st_);
+      cudaFreeAsync(dt_.list, st_); cudaFreeAsync(dt_.klist, st_);
     }
-    if (pt_.ent) { dfree(pt_.ent); dfree(pt_.lists); }
-    if (sc_.a) { dfree(sc_.a); dfree(sc_.b); }
+    if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.lists, st_); }
+    if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
     if (recs_) cudaFreeHost(recs_);
     if (ctrl_) cudaFreeHost(ctrl_);
-    if (ctr_) dfree(ctr_);
+    if (ctr_) cudaFreeAsync(ctr_, st_);
     if (st_) cudaStreamSynchronize(st_);
     if (st_copy_) { cudaStreamDestroy(st_copy_); st_copy_ = nullptr; }
     dist_teardown();
