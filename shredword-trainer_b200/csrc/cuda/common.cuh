@@ -41,8 +41,8 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __device__ __forceinline__ bool is_delim(uint32_t c) { return c <= 32u && ((0x100002600ull >> c) & 1ull); }  // \t \n \r space
 
 // ---- device -> host wire formats (mapped pinned host memory) -------------------------------------------------------
-// The device never fences towards the host.  Everything it publishes is written as 16-byte vector stores (one PCIe write each)
-// that carry the pass's 32-bit tag themselves, and the host accepts a block only when it sees the current tag in it: no
+// The device never fences towards the host.  Everything it publishes is made of 16-byte blocks that carry the pass's 32-bit
+// tag themselves (written two at a time with one 256-bit store = one PCIe write), and the host accepts a block only when it sees the current tag in it: no
 // ordering between different stores, threads or CTAs is assumed, so no __threadfence_system() sits on the per-merge path.
 //   WireRec  w0 = key | w1 = val (48 bits) + tag low half << 48 || w2 = seq (48 bits) + tag high half << 48 | w3 = kind/list length + serial << 32
 //   Ctrl     block 0: tag + n_recs << 32 | err + list_len << 32     block 1: tag + occ_local << 32 | occ_global
@@ -51,16 +51,18 @@ struct WireRec { ull w[4]; };
 struct Ctrl { ull w[8]; };
 constexpr ull MASK48 = (1ull << 48) - 1ull;
 __device__ __forceinline__ void st_wire(void* p, ull x, ull y) { asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory"); }
+// 32 bytes with one 256-bit store (sm_100): one PCIe write per record instead of two -- the host still checks both halves
+__device__ __forceinline__ void st_wire32(void* p, ull x, ull y, ull z, ull w) {
+  asm volatile("st.volatile.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(x), "l"(y), "l"(z), "l"(w) : "memory");
+}
 __device__ __forceinline__ void wire_rec(WireRec* r, uint32_t tag, uint64_t key, uint64_t val, uint64_t seq, uint32_t kind, uint32_t serial) {
-  st_wire(&r->w[0], key, (val & MASK48) | (static_cast<ull>(tag & 0xFFFFu) << 48));
-  st_wire(&r->w[2], (seq & MASK48) | (static_cast<ull>(tag >> 16) << 48), static_cast<ull>(kind) | (static_cast<ull>(serial) << 32));
+  st_wire32(&r->w[0], key, (val & MASK48) | (static_cast<ull>(tag & 0xFFFFu) << 48), (seq & MASK48) | (static_cast<ull>(tag >> 16) << 48),
+            static_cast<ull>(kind) | (static_cast<ull>(serial) << 32));
 }
 __device__ __forceinline__ void wire_ctrl(Ctrl* c, uint32_t tag, uint32_t n_recs, uint32_t err, uint32_t list_len, uint32_t occ_local, ull occ_global, uint32_t n_keys, ull pt_n,
                                           ull pool_top) {
-  st_wire(&c->w[2], tag | (static_cast<ull>(occ_local) << 32), occ_global);
-  st_wire(&c->w[4], tag | (static_cast<ull>(n_keys) << 32), pt_n);
-  st_wire(&c->w[6], tag, pool_top);
-  st_wire(&c->w[0], tag | (static_cast<ull>(n_recs) << 32), err | (static_cast<ull>(list_len) << 32));
+  st_wire32(&c->w[4], tag | (static_cast<ull>(n_keys) << 32), pt_n, tag, pool_top);
+  st_wire32(&c->w[0], tag | (static_cast<ull>(n_recs) << 32), err | (static_cast<ull>(list_len) << 32), tag | (static_cast<ull>(occ_local) << 32), occ_global);
 }
 
 // Device counters.  The per-pass counters exist twice: pass number e uses [e & 1] and zeroes [(e + 1) & 1] for its successor

@@ -293,12 +293,6 @@ __device__ __forceinline__ bool small_merge_body(SmallStage& s, const MergeArgs&
   // ---- phase 2: fold, 32 keys per warp at a time
   const uint32_t n_keys = s.n_keys, n_occ = s.n_occ;
   const uint32_t err_before = *reinterpret_cast<volatile uint32_t*>(&ctr->err);  // consumed at the very end
-  if (t == nt - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0
-    const uint64_t k = fc_key(a.A, a.B);
-    uint64_t old;
-    const uint64_t sl = pt_find_or_insert(a.pt, ctr, k, ld_ent(&a.pt.ent[mix64(k) & a.pt.mask]), &old);
-    a.pt.ent[sl].freq = 0ull;
-  }
   const uint32_t lt = (1u << lane) - 1u;
   for (uint32_t i0 = (t >> 5) * 32u; i0 < n_keys; i0 += (nt >> 5) * 32u) {
     const uint32_t i = i0 + lane;
@@ -396,6 +390,10 @@ __device__ __forceinline__ bool small_merge_body(SmallStage& s, const MergeArgs&
     if (a.dbg) a.dbg[2] = gtime();
   }
   // ---- phase 3: rewrite the occurrences, fill the new pairs' lists (the host is already replaying its heap)
+  if (t == nt - 1) {  // bpe.cpp:315: the merged pair's frequency becomes 0.  Nothing reads that entry before the next count pass
+    const uint64_t sl = pt_lookup(a.pt, fc_key(a.A, a.B));  // (a new adjacency always contains a new token), so it is kept off the path to the publish
+    if (sl != ~0ull) a.pt.ent[sl].freq = 0ull;              // (the host only merges pairs the table holds: its entry exists)
+  }
   int32_t* idsw = a.ids;
   auto st = [idsw](uint64_t q, int32_t v2) { idsw[q] = v2; };
   for (uint32_t i = t; i < n_occ; i += nt) {
@@ -441,23 +439,20 @@ __global__ void __launch_bounds__(1024) k_merge_server(MergeArgs a, const Server
   ull next = first_seq;
   small_clear(s, SMALL_SLOTS_MAX, a.dt.empty);  // the poll loop's barrier below separates this from the first merge
   for (;;) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32u) {  // warp 0 polls together: lanes 0-3 read one 16-byte quarter each with ONE instruction (one 64-byte PCIe read per poll)
+      const uint32_t ln = threadIdx.x;
       const ull t0 = gtime();
-      op = SRV_OP_QUIT;
+      if (ln == 0) op = SRV_OP_QUIT;
       for (;;) {
-        ull q[8];
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[0]), "=l"(q[1]) : "l"(&cmd->w[0]));
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[2]), "=l"(q[3]) : "l"(&cmd->w[2]));
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[4]), "=l"(q[5]) : "l"(&cmd->w[4]));
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[6]), "=l"(q[7]) : "l"(&cmd->w[6]));
+        ull x = 0, y = 0;
+        if (ln < 4u) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(&cmd->w[2u * ln]));
         const ull want = next & 0xFFFFFFFFull;
-        if ((q[1] >> 32) == want && (q[3] >> 32) == want && (q[5] >> 32) == want && (q[7] >> 32) == want) {
-#pragma unroll
-          for (int k = 0; k < 8; k++) c[k] = q[k];
-          op = static_cast<uint32_t>(q[1] & 0xFFFFFFFFull);
+        if (__all_sync(0xFFFFFFFFu, ln >= 4u || (y >> 32) == want)) {
+          if (ln < 4u) { c[2u * ln] = x; c[2u * ln + 1u] = y; }
+          if (ln == 0) op = static_cast<uint32_t>(y & 0xFFFFFFFFull);
           break;
         }
-        if (gtime() - t0 > SERVER_IDLE_NS) break;  // nobody is talking to us any more
+        if (__any_sync(0xFFFFFFFFu, gtime() - t0 > SERVER_IDLE_NS)) break;  // nobody is talking to us any more
       }
     }
     __syncthreads();

@@ -328,6 +328,7 @@ int TrainerCore::merge_loop(int batch_size) {
     h_open = now_ms();
     apply_records(recs, n);
     ++ver_of(top.serial, k);  // bpe.cpp:315-316
+    { const double t_applied = now_ms(); host_apply_ms_ += t_applied - h_open; host_heap_ms_ += t_applied - h_open; h_open = t_applied; }
     occurrences_ += occ;
     abi_->num_merges++;
     done++;
@@ -341,7 +342,7 @@ int TrainerCore::train() {  // bpe.cpp:345-386
   SHRED_RANGE("bpe_train");
   double t0 = now_ms();
   eng_->mark_begin();
-  host_heap_ms_ = 0; host_pop_ms_ = 0; occurrences_ = 0;
+  host_heap_ms_ = 0; host_pop_ms_ = 0; host_apply_ms_ = 0; occurrences_ = 0;
   heap_.pushes = heap_.pops = 0;
   tie_root_equal_ = tie_same_as_prev_ = 0; last_merge_freq_ = ~0ull;
   heap_.set_tracking(false);  // one rebuild of the Trainer.heap mirror at the end instead of noting every written slot
@@ -364,8 +365,8 @@ int TrainerCore::train() {  // bpe.cpp:345-386
   if (!quiet_) std::printf("[INFO]\t Training completed. Performed %d merges\n", total);
   if (const char* dbg = std::getenv("SHRED_DEBUG_TIMING")) if (*dbg && *dbg != '0') {
     EngineStats es; std::memset(&es, 0, sizeof es); eng_->stats(&es);
-    std::fprintf(stderr, "[TIMING]\t train %.1f ms (device %.1f): engine.merge %.1f (launch %.1f, wait %.1f), host heap %.1f (of which pops until a current entry %.1f), merges %d, pushes %llu pops %llu\n",
-                 train_wall_ms_, train_device_ms_, es.merge_ms, es.launch_ms, es.wait_ms, host_heap_ms_, host_pop_ms_, total,
+    std::fprintf(stderr, "[TIMING]\t train %.1f ms (device %.1f): engine.merge %.1f (launch %.1f, wait %.1f), host heap %.1f (pops until a current entry %.1f, records applied %.1f), merges %d, pushes %llu pops %llu\n",
+                 train_wall_ms_, train_device_ms_, es.merge_ms, es.launch_ms, es.wait_ms, host_heap_ms_, host_pop_ms_, host_apply_ms_, total,
                  static_cast<unsigned long long>(heap_.pushes), static_cast<unsigned long long>(heap_.pops));
   }
   sync_mirrors();

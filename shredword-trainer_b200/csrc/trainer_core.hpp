@@ -66,7 +66,7 @@ class TrainerCore {
   // statistics of the last load/train
   uint64_t occurrences_ = 0, merges_last_ = 0, corpus_bytes_ = 0;
   uint64_t tie_root_equal_ = 0, tie_same_as_prev_ = 0, last_merge_freq_ = ~0ull;
-  double load_wall_ms_ = 0, train_wall_ms_ = 0, train_device_ms_ = 0, host_heap_ms_ = 0, host_pop_ms_ = 0, save_wall_ms_ = 0;
+  double load_wall_ms_ = 0, train_wall_ms_ = 0, train_device_ms_ = 0, host_heap_ms_ = 0, host_pop_ms_ = 0, host_apply_ms_ = 0, save_wall_ms_ = 0;
   bool log_merges_ = false, quiet_ = false;
   FILE* trace_file_ = nullptr;
 };

@@ -1,9 +1,10 @@
 # one-off A/B helper (not a test): bench variants of the library (environment knobs / build/libtrainer_base.so) on the same box
-# usage: bash tests/ab_env_bench.sh <workload> <steps> <warmup> "<label>:<ENV=1 ...>" ...   (label "base" uses build/libtrainer_base.so)
+# usage: bash tests/ab_env_bench.sh <workload> <steps> <warmup> "<label>:<ENV=1 ...>" ...   (label "base" uses build/libtrainer_base.so, labels "alt*" build/libtrainer_<label>.so)
 W=$1; S=$2; WU=$3; shift 3
 for round in 1 2; do for spec in "$@"; do
   label=${spec%%:*}; envs=${spec#*:}
   ( if [ "$label" = base ]; then export SHRED_LIBTRAINER=$PWD/shredword-trainer_b200/build/libtrainer_base.so; fi
+    case "$label" in alt*) export SHRED_LIBTRAINER=$PWD/shredword-trainer_b200/build/libtrainer_$label.so;; esac
     for e in $envs; do export $e; done
     python bench.py --workload $W --steps $S --warmup $WU --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
