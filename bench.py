@@ -315,6 +315,7 @@ def main():
             os.environ.pop(k, None)
         if as_shard:
             os.environ.update(shard_env)
+        tc = time.perf_counter()
         t = BPETrainer(vocab, unk, cov, mf)
         t0 = time.perf_counter()
         if buffer is None:
@@ -327,9 +328,11 @@ def main():
         t.save(model_path, vocab_path)     # bpe_save: token frequencies from the device, both files written
         t3 = time.perf_counter()
         st = t.stats()
+        t4 = time.perf_counter()
         t.destroy()
+        t5 = time.perf_counter()
         out_bytes = os.path.getsize(model_path) + os.path.getsize(vocab_path)
-        return {"merges": n, "load_s": t1 - t0, "train_s": t2 - t1, "save_s": t3 - t2, "st": st, "out_bytes": out_bytes}
+        return {"merges": n, "load_s": t1 - t0, "train_s": t2 - t1, "save_s": t3 - t2, "create_s": t0 - tc, "destroy_s": t5 - t4, "st": st, "out_bytes": out_bytes}
 
     import contextlib
     import io
@@ -429,6 +432,8 @@ def main():
                 "what": "bpe_load_corpus(path) + bpe_train + bpe_save through the drop-in C ABI (the reference's call sequence, shredword/trainer.py:12-29); corpus file in host "
                         "memory (tmpfs), both output files written; max over ranks",
                 "load_s_per_step": phase[0], "train_s_per_step": phase[1], "save_s_per_step": phase[2],
+                "create_destroy_s_per_step": {"create_trainer": sum(x["create_s"] for x in steps) / len(steps), "bpe_trainer_destroy": sum(x["destroy_s"] for x in steps) / len(steps),
+                                              "what": "rank 0's create_trainer / bpe_trainer_destroy around every step; not part of value or e2e.value, part of ms_per_step"},
                 "cold_first_step": {"load_s": cold["load_s"], "train_s": cold["train_s"], "save_s": cold["save_s"],
                                     "what": "first step of the process (warm-up 0): allocator pool growth, pinned staging ring, lazy module load included"} if cold else None,
                 "load_buffer_variant": side_buffer},

@@ -119,6 +119,38 @@ struct VirtualCluster {
   }
 };
 
+// Mapped pinned host blocks (control block, record buffer, server command block) are kept for the life of the process and handed
+// from one trainer to the next: cudaHostAlloc / cudaFreeHost pin and unpin pages and synchronise the device -- 90 ms per
+// create_trainer and 270-370 ms per bpe_trainer_destroy at the 10 GB configuration before this cache.  A block is returned only
+// after its trainer's streams have drained, and every user clears it before use (stale pass tags must not look valid).
+class PinnedCache {
+ public:
+  static PinnedCache& get() { static PinnedCache c; return c; }
+  void* acquire(size_t bytes) {
+    bytes = (bytes + 4095) & ~static_cast<size_t>(4095);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      size_t best = free_.size();
+      for (size_t i = 0; i < free_.size(); i++)
+        if (free_[i].second >= bytes && free_[i].second <= 4 * bytes && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+      if (best != free_.size()) { void* p = free_[best].first; free_.erase(free_.begin() + static_cast<std::ptrdiff_t>(best)); return p; }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+  }
+  void release(void* p, size_t bytes) {
+    if (!p) return;
+    bytes = (bytes + 4095) & ~static_cast<size_t>(4095);
+    std::lock_guard<std::mutex> g(mu_);
+    free_.emplace_back(p, bytes);
+  }
+
+ private:
+  std::mutex mu_;
+  std::vector<std::pair<void*, size_t>> free_;
+};
+
 class CudaEngine : public Engine {
  public:
   CudaEngine(int dev, const cudaDeviceProp& prop) : dev_(dev), n_sm_(prop.multiProcessorCount > 0 ? prop.multiProcessorCount : N_SM_FALLBACK) {
@@ -129,8 +161,8 @@ class CudaEngine : public Engine {
   int init() {
     CK(cudaSetDevice(dev_));
     CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
-    void* cp = nullptr;
-    CK(cudaHostAlloc(&cp, sizeof(Ctrl), cudaHostAllocMapped));
+    void* cp = PinnedCache::get().acquire(sizeof(Ctrl));
+    if (!cp) { std::fprintf(stderr, "[ERROR]\t no pinned host memory\n"); return -1; }
     std::memset(cp, 0, sizeof(Ctrl));
     ctrl_ = static_cast<Ctrl*>(cp);
     CK(cudaMallocAsync(reinterpret_cast<void**>(&ctr_), sizeof(DevCounters), st_));
@@ -143,8 +175,8 @@ class CudaEngine : public Engine {
     cudaMemPool_t pool;  // stream-ordered allocations; keep freed blocks cached so repeated loads do not pay cudaMalloc
     if (cudaDeviceGetDefaultMemPool(&pool, dev_) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
     {  // in-kernel phase timestamps (%globaltimer) of the timed launches
-      void* dp = nullptr;
-      CK(cudaHostAlloc(&dp, 32 * sizeof(ull), cudaHostAllocMapped));
+      void* dp = PinnedCache::get().acquire(32 * sizeof(ull));
+      if (!dp) { std::fprintf(stderr, "[ERROR]\t no pinned host memory\n"); return -1; }
       dbg_ = static_cast<ull*>(dp);
       std::memset(dp, 0, 32 * sizeof(ull));
       const char* d = std::getenv("SHRED_DEBUG_TIMING");
@@ -156,8 +188,8 @@ class CudaEngine : public Engine {
     CK(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallStage))));
     CK(cudaFuncSetAttribute(k_merge_server, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmallStage))));
     {
-      void* sp = nullptr;
-      CK(cudaHostAlloc(&sp, sizeof(ServerCmd) + 64, cudaHostAllocMapped));
+      void* sp = PinnedCache::get().acquire(sizeof(ServerCmd) + 64);
+      if (!sp) { std::fprintf(stderr, "[ERROR]\t no pinned host memory\n"); return -1; }
       std::memset(sp, 0, sizeof(ServerCmd) + 64);
       srv_cmd_ = static_cast<ServerCmd*>(sp);
       srv_done_ = reinterpret_cast<ServerDone*>(static_cast<uint8_t*>(sp) + sizeof(ServerCmd));
@@ -608,9 +640,10 @@ class CudaEngine : public Engine {
     launches_++;
     // the record buffer holds at most one record per key of a pass; callers fetch recs_ only after the last possible growth
     if (!recs_ || rec_cap_ < dt_.cap) {
-      if (recs_) { CK(cudaStreamSynchronize(st_)); cudaFreeHost(recs_); recs_ = nullptr; }
+      if (recs_) { CK(cudaStreamSynchronize(st_)); PinnedCache::get().release(recs_, static_cast<size_t>(rec_cap_) * sizeof(WireRec)); recs_ = nullptr; }
       rec_cap_ = dt_.cap;
-      CK(cudaHostAlloc(reinterpret_cast<void**>(&recs_), static_cast<size_t>(rec_cap_) * sizeof(WireRec), cudaHostAllocMapped));
+      recs_ = static_cast<WireRec*>(PinnedCache::get().acquire(static_cast<size_t>(rec_cap_) * sizeof(WireRec)));
+      if (!recs_) { std::fprintf(stderr, "[ERROR]\t no pinned host memory for %u records\n", rec_cap_); rec_cap_ = 0; return -1; }
       std::memset(recs_, 0, static_cast<size_t>(rec_cap_) * sizeof(WireRec));  // tag 0 = never written (pass tags start at 1)
     }
     return 0;
@@ -1113,6 +1146,7 @@ class CudaEngine : public Engine {
       std::fprintf(stderr, "[KTIME]\t %llu timed merges: probe+emit+barrier %.1f us, fold+publish %.1f us, rewrite %.1f us | kernel (events) %.1f us (averages)\n",
                    (unsigned long long)dbg_n_, 1e3 * dbg_acc_[0] / dbg_n_, 1e3 * dbg_acc_[1] / dbg_n_, 1e3 * dbg_acc_[2] / dbg_n_, 1e3 * dbg_acc_[3] / dbg_n_);
     }
+    const double tr0 = now_ms();
     release_corpus();
     if (dt_.keys) {
       cudaFreeAsync(dt_.keys, st_); cudaFreeAsync(dt_.delta, st_); cudaFreeAsync(dt_.seq, st_); cudaFreeAsync(dt_.nocc, st_); cudaFreeAsync(dt_.base, st_);
@@ -1120,14 +1154,19 @@ class CudaEngine : public Engine {
     }
     if (pt_.ent) { cudaFreeAsync(pt_.ent, st_); cudaFreeAsync(pt_.lists, st_); }
     if (sc_.a) { cudaFreeAsync(sc_.a, st_); cudaFreeAsync(sc_.b, st_); }
-    if (recs_) cudaFreeHost(recs_);
-    if (ctrl_) cudaFreeHost(ctrl_);
     if (ctr_) cudaFreeAsync(ctr_, st_);
+    const double tr1 = now_ms();
     if (st_) cudaStreamSynchronize(st_);
+    const double tr2 = now_ms();
+    if (dbg_print_) std::fprintf(stderr, "[TIMING]\t engine release: frees %.1f ms, stream sync %.1f ms\n", tr1 - tr0, tr2 - tr1);
     if (st_copy_) { cudaStreamDestroy(st_copy_); st_copy_ = nullptr; }
     dist_teardown();
-    if (srv_cmd_) cudaFreeHost(srv_cmd_);
-    if (st_srv_) cudaStreamDestroy(st_srv_);
+    if (st_srv_) { cudaStreamSynchronize(st_srv_); cudaStreamDestroy(st_srv_); }
+    // nothing of this trainer can write to its pinned blocks any more: hand them to the next one
+    PinnedCache::get().release(recs_, static_cast<size_t>(rec_cap_) * sizeof(WireRec)); recs_ = nullptr;
+    PinnedCache::get().release(ctrl_, sizeof(Ctrl)); ctrl_ = nullptr;
+    PinnedCache::get().release(dbg_, 32 * sizeof(ull)); dbg_ = nullptr;
+    PinnedCache::get().release(srv_cmd_, sizeof(ServerCmd) + 64); srv_cmd_ = nullptr;
     if (ev_srv_) cudaEventDestroy(ev_srv_);
     if (ev_gen_) cudaEventDestroy(ev_gen_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -1212,8 +1251,18 @@ Engine* make_device_engine() {
   if (const char* s = std::getenv("SHRED_DEVICE")) dev = std::atoi(s);
   else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   if (dev < 0 || dev >= n) dev = 0;
+  // cudaGetDeviceProperties takes tens of milliseconds (it queries clocks and the board): once per device and process
+  static std::mutex prop_mu;
+  static cudaDeviceProp props[64];
+  static bool have[64] = {false};
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return nullptr;
+  {
+    std::lock_guard<std::mutex> g(prop_mu);
+    if (dev >= 64 || !have[dev]) {
+      if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return nullptr;
+      if (dev < 64) { props[dev] = prop; have[dev] = true; }
+    } else prop = props[dev];
+  }
   if (prop.major != 10) {
     std::fprintf(stderr, "[ERROR]\t CUDA: device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library carries sm_100a code only\n", dev, prop.name,
                  prop.major, prop.minor);

@@ -74,11 +74,16 @@ TrainerCore::TrainerCore(Trainer* abi, Engine* eng) : abi_(abi), eng_(eng) {
 }
 
 TrainerCore::~TrainerCore() {
+  const char* dbg = std::getenv("SHRED_DEBUG_TIMING");
+  const bool timing = dbg && *dbg && *dbg != '0';
+  const double t0 = now_ms();
   if (trace_file_) std::fclose(trace_file_);
   std::free(abi_->merge_ops); abi_->merge_ops = nullptr;
   std::free(abi_->corpus.words); abi_->corpus.words = nullptr;
   std::free(abi_->corpus.word_counts); abi_->corpus.word_counts = nullptr;
+  const double t1 = now_ms();
   delete eng_;
+  if (timing) std::fprintf(stderr, "[TIMING]\t destroy: host mirrors %.1f ms, engine %.1f ms (the heap and version tables follow)\n", t1 - t0, now_ms() - t1);
 }
 
 void TrainerCore::sync_mirrors() {  // Trainer.heap in the reference's layout (rebuilt only if the heap changed)
