@@ -417,8 +417,9 @@ __global__ void __launch_bounds__(1024) k_merge_small(const MergeArgs a, const u
 // A launch costs the host ~3 us of API time and the device ~3-5 us before the first instruction runs, with a cold instruction
 // cache -- as much as the work of a short merge itself.  While the host replays its heap, ONE CTA therefore stays resident
 // (k_merge_server, 1024 threads, its own stream) and takes short merges as 64-byte commands from mapped host memory: the host
-// writes (A, B, N, lengths, serial, list length, tag), the CTA polls the block (one PCIe read round trip per poll, all four
-// 16-byte quarters in flight together; a command is accepted when the sequence number in its first and last quarter agree),
+// writes (A, B, N, lengths, serial, list length, tag), warp 0 of the CTA polls the block -- four lanes read one 16-byte quarter
+// each with ONE load instruction, i.e. one 64-byte PCIe read per poll: polling with four separate reads cost 2.8 us more per
+// merge, polling from eight threads 15 us more (non-posted reads queue up) -- and the CTA
 // runs small_merge_body and reports the end of phase 3 in a second self-validating block, after which the host may run other
 // kernels on the data.  The server leaves when told to (end of bpe_merge_batch / bpe_train, any other operation) or after
 // SERVER_IDLE_NS without a command -- it can never outlive a dead host by more than that.
