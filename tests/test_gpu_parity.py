@@ -265,6 +265,40 @@ def test_two_trainers_interleaved(T):
     a.destroy(); b.destroy()
 
 
+def test_trainers_in_concurrent_threads(T, tmp_path):
+    """four host threads of one process, each with its own trainer on the same GPU (load, train, save, destroy, twice over):
+    every trainer keeps its own resident merge server, the cooperative launches size their grids for the SMs the servers
+    hold, the pinned blocks and the staging ring are shared process-wide -- and every result equals the golden one"""
+    import threading
+    names = ("zipf2m_0", "multi600k_1", "zipf2m_3", "multi600k_2")
+    cases = [[c for c in GOLDEN if c["name"] == nm][0] for nm in names]
+    errors = []
+
+    def work(i, case):
+        try:
+            for rnd in range(2):
+                path = str(tmp_path / ("c%d_%d.txt" % (i, rnd)))
+                open(path, "wb").write(corpus_bytes(case))
+                t = T(*case["config"])
+                t.load_corpus(path) if rnd else t.load_bytes(corpus_bytes(case))
+                assert t.train() == case["merges"]
+                assert md5(_merge_bytes(t.merges())) == case["merges_md5"]
+                t.save(str(tmp_path / ("m%d.bin" % i)), str(tmp_path / ("v%d.txt" % i)))
+                if case["vocab_md5"] is not None:
+                    assert md5(open(str(tmp_path / ("v%d.txt" % i)), "rb").read()) == case["vocab_md5"]
+                t.destroy()
+        except BaseException as e:  # noqa: BLE001 -- reported by the main thread
+            errors.append((case["name"], repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i, c)) for i, c in enumerate(cases)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not any(th.is_alive() for th in threads), "a trainer thread hangs"
+    assert not errors, errors
+
+
 def test_load_corpus_from_file_paths(T, tmp_path):
     """bpe_load_corpus(path) streams the file through the pinned staging ring; a file with NUL bytes falls back to the
     host-side blanking pass; an empty file loads; sizes around the 32 MiB staging chunk are covered by a 70 MB file"""
