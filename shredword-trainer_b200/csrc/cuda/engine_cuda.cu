@@ -786,6 +786,7 @@ class CudaEngine : public Engine {
     k_merge_server<<<1, 1024, sizeof(SmallStage), st_srv_>>>(ma, srv_cmd_, srv_done_, srv_seq_);
     CK(cudaGetLastError());
     launches_++; srv_starts_++;
+    srv_cmds_since_start_ = 0;
     srv_alive_ = true; srv_busy_ = false;
     live_servers().fetch_add(1);
     return 0;
@@ -870,8 +871,18 @@ class CudaEngine : public Engine {
         srv_tag_ = static_cast<uint32_t>(flag_); srv_busy_ = true;
         launch_ms_ += now_ms() - tl0;
         const int wrc = wait_flag();
-        if (wrc == 2) { cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; live_servers().fetch_sub(1); continue; }  // the server left just before the command: start it again
+        if (wrc == 2) {  // the server left just before the command: start it again
+          cudaStreamSynchronize(st_srv_); srv_alive_ = false; srv_busy_ = false; live_servers().fetch_sub(1);
+          // A server that leaves before its FIRST command, twice in a row, never ran beside the host: kernel launches are being
+          // serialised (ncu, compute-sanitizer, cuda-gdb, CUDA_LAUNCH_BLOCKING=1).  Short merges become launches for this trainer.
+          if (srv_cmds_since_start_ == 0 && ++srv_stillborn_ >= 2) {
+            srv_enabled_ = false;
+            std::fprintf(stderr, "[WARN]\t the resident merge server cannot run beside the host here (serialised kernel launches?): using one launch per merge\n");
+          }
+          continue;
+        }
         if (wrc != 0) return wrc;
+        ++srv_cmds_since_start_; srv_stillborn_ = 0;
         ++srv_seq_;
         srv_ms = now_ms() - tl0;
         srv_merges_++;
@@ -1215,6 +1226,8 @@ class CudaEngine : public Engine {
   cudaStream_t st_srv_ = nullptr;
   cudaEvent_t ev_srv_ = nullptr, ev_gen_ = nullptr;
   bool srv_enabled_ = true, srv_alive_ = false, srv_busy_ = false, general_pending_ = false;
+  uint64_t srv_cmds_since_start_ = 0;  // commands the running server has taken
+  int srv_stillborn_ = 0;              // consecutive servers that left without taking one
   uint64_t srv_seq_ = 0, srv_merges_ = 0, srv_starts_ = 0;
   uint32_t srv_tag_ = 0;
   uint32_t small_max_ = SMALL_MAX;

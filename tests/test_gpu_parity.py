@@ -299,6 +299,29 @@ def test_trainers_in_concurrent_threads(T, tmp_path):
     assert not errors, errors
 
 
+def test_serialised_launches_fall_back_to_one_launch_per_merge(native, tmp_path):
+    """under a tool that serialises kernel launches (here CUDA_LAUNCH_BLOCKING=1; ncu and compute-sanitizer do the same) the
+    resident merge server can never run beside the host: the trainer notices (two servers in a row leave before their first
+    command), says so once and does every merge as a launch -- same merges"""
+    import sys
+    case = [c for c in GOLDEN if c["name"] == "kat_cpp"][0]
+    corpus = tmp_path / "c.txt"
+    corpus.write_bytes(corpus_bytes(case))
+    code = (
+        "import sys, struct, hashlib; sys.path.insert(0, %r)\n"
+        "from shredword import BPETrainer\n"
+        "t = BPETrainer(*%r); t.load_corpus(%r); n = t.train()\n"
+        "print(n, hashlib.md5(b''.join(struct.pack('<3i', *m) for m in t.merges())).hexdigest(), int(t.stats()['server_merges']))\n"
+        "t.destroy()\n"
+    ) % (os.path.join(os.path.dirname(os.path.dirname(__file__)), "shredword-trainer_b200"), tuple(case["config"]), str(corpus))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", SHRED_QUIET="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n, digest, served = r.stdout.split()[-3:]
+    assert int(n) == case["merges"] and digest == case["merges_md5"] and int(served) == 0
+    assert "resident merge server cannot run" in r.stderr
+
+
 def test_load_corpus_from_file_paths(T, tmp_path):
     """bpe_load_corpus(path) streams the file through the pinned staging ring; a file with NUL bytes falls back to the
     host-side blanking pass; an empty file loads; sizes around the 32 MiB staging chunk are covered by a 70 MB file"""
